@@ -1,0 +1,68 @@
+"""CPU: the oracle (oracle/disco_oracle.py) against fixtures generated from the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle; GPU parity tests then compare the CUDA path
+with the oracle and with the same fixtures."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, GOLDEN, golden_cases, load_golden, case_inputs
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import disco_oracle as O  # noqa: E402
+
+TOL = 2e-4   # fp32 CPU conv kernels may differ across hosts (thread count / ISA); same host gives 0.0
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_oracle_matches_reference_fixture(case, synth_sd):
+    torch.set_flush_denormal(True)
+    g = load_golden(case["name"])
+    gray, ab = (torch.from_numpy(t) for t in case_inputs(case))
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    with torch.no_grad():
+        pal, ref, pred, aff, spix, hint = O.forward(synth_sd, gray, ab, case["K"], case["T"])
+    st = int(g["affinity_stride"])
+    assert np.array_equal(hint.numpy(), g["hint_mask"]), "anchor sites differ from the reference"
+    assert np.abs(aff.numpy()[:, :, ::st, ::st] - g["affinity"]).max() < TOL
+    assert np.abs(pal.numpy() - g["pal_logit"]).max() < 50 * TOL      # logits are O(10)
+    assert np.abs(ref.numpy() - g["ref_logit"]).max() < 50 * TOL
+    assert np.abs(spix.numpy() - g["spix_colors"]).max() < 1e-6
+    assert np.abs(pred.numpy() - g["pred_colors"]).max() < 1e-3       # north-star fp32 tolerance on ab
+    # RNG streams were consumed exactly as the reference consumes them
+    assert int(np.random.randint(1 << 30)) == int(g["np_next"])
+    assert int(torch.randint(1 << 30, (1,))) == int(g["torch_next"])
+
+
+def test_gamut_table_properties():
+    from disentangledcolorization_b200.cielab import Q_TO_AB
+    assert Q_TO_AB.shape == (313, 2) and Q_TO_AB.dtype == np.float32
+    assert np.all(Q_TO_AB % 10 == 0)
+    order = np.lexsort((Q_TO_AB[:, 1], Q_TO_AB[:, 0]))
+    assert np.array_equal(order, np.arange(313))           # sorted by (a, b) like ab[mask]
+    assert Q_TO_AB[:, 0].min() == -90 and Q_TO_AB[:, 0].max() == 100
+    assert Q_TO_AB[:, 1].min() == -110 and Q_TO_AB[:, 1].max() == 100
+
+
+def test_encode_argmax_is_nearest_bin():
+    """argmax(encode_ab2ind(x)) == nearest gamut bin."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    ab = torch.from_numpy((rng.random((3, 2, 5, 7), dtype=np.float32) - 0.5) * 0.8)  # well inside the gamut hull
+    lab = O.encode_ab2ind(ab).max(dim=1)[1]
+    table = O.q_to_ab()
+    d = torch.cdist((ab * 110).permute(0, 2, 3, 1).reshape(-1, 2), table)
+    assert torch.equal(lab.flatten(), d.argmin(1))
+
+
+def test_state_dict_schema_matches_reference():
+    from disentangledcolorization_b200 import netspec
+    with open(os.path.join(GOLDEN, "state_dict_schema.json")) as f:
+        ref = json.load(f)
+    mine = {k: (list(s), p) for k, s, p in netspec.schema()}
+    assert len(mine) == len(ref) == 461
+    for k, s, p in ref:
+        assert mine[k] == (s, p), k
