@@ -1,0 +1,106 @@
+"""ctypes binding of libdisco_b200.so (the C ABI declared in include/disco_b200.h).
+
+There is no fallback: if the library is missing or the device is not a B200 the import of the
+compute path raises.  Set DISCO_B200_BUILD=1 to (re)build with nvcc on first use.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdisco_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+HEAD_NONE, HEAD_SOFTMAX9, HEAD_TANH2 = 0, 1, 2
+CONV3, DECONV4 = 0, 1
+
+EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
+           "disco_reset_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
+           "disco_attention", "disco_kmeans_anchor", "disco_token_labels"]
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("up2", C.c_int32),
+                ("is_f32", C.c_int32), ("w_off", C.c_int64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("stride", C.c_int32), ("dtype", C.c_int32), ("batch", C.c_int32),
+                ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("n_src", C.c_int32),
+                ("src", ConvSrc * 2), ("weights", C.c_void_p), ("bias", C.c_void_p), ("post_scale", C.c_void_p),
+                ("post_shift", C.c_void_p), ("residual", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float),
+                ("head", C.c_int32), ("out", C.c_void_p)]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("X", C.c_void_p), ("W", C.c_void_p), ("b", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
+                ("K", C.c_int32), ("pos", C.c_void_p), ("pos_cols", C.c_int32), ("S", C.c_int32),
+                ("col_scale", C.c_float), ("scale_cols", C.c_int32), ("relu", C.c_int32), ("residual", C.c_void_p),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("hint_mask", C.c_void_p), ("labels", C.c_void_p),
+                ("emb", C.c_void_p), ("transpose_S", C.c_int32), ("Y", C.c_void_p)]
+
+
+_lib = None
+
+
+class DiscoError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (building it first when DISCO_B200_BUILD=1).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("DISCO_B200_BUILD") == "1":
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise DiscoError(f"{LIB_PATH} not found: build it with `python -m disentangledcolorization_b200.build` "
+                         "(there is no CPU / PyTorch fallback for the compute path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.disco_last_error.restype = C.c_char_p
+    lib.disco_launch_count.restype = C.c_int64
+    lib.disco_launch_count.argtypes = [C.c_void_p]
+    lib.disco_reset_launch_count.argtypes = [C.c_void_p]
+    lib.disco_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.disco_destroy.argtypes = [C.c_void_p]
+    lib.disco_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]
+    lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
+    lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
+    lib.disco_linear.argtypes = [C.c_void_p, C.POINTER(LinearDesc), C.c_void_p]
+    lib.disco_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.disco_kmeans_anchor.argtypes = ([C.c_void_p] * 4 + [C.c_int, C.c_void_p] + [C.c_int] * 4 + [C.c_float]
+                                        + [C.c_void_p] * 5)
+    lib.disco_token_labels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, what="disco call"):
+    if rc != 0:
+        raise DiscoError(f"{what} failed ({rc}): {load().disco_last_error().decode()}")
+
+
+class Handle:
+    """One library handle per (process, device)."""
+    _cache = {}
+
+    def __init__(self, device_index):
+        lib = load()
+        h = C.c_void_p()
+        check(lib.disco_create(C.byref(h), int(device_index)), "disco_create")
+        self.lib, self.h, self.device_index = lib, h, int(device_index)
+
+    @classmethod
+    def get(cls, device_index):
+        if device_index not in cls._cache:
+            cls._cache[device_index] = cls(device_index)
+        return cls._cache[device_index]
+
+    def launches(self):
+        return int(self.lib.disco_launch_count(self.h))
+
+    def reset_launches(self):
+        self.lib.disco_reset_launch_count(self.h)

@@ -1,0 +1,117 @@
+"""Drop-in `basic` module: the free functions and ColorLabel that callers of the forward path use
+directly (reference main/colorizer/inference.py:114-115,119,129; models/basic.py:10-12,149-218,
+274-376).  NCHW fp32 tensors in and out, CUDA only; arithmetic runs in libdisco_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cielab import Q_TO_AB
+
+
+def tensor2array(tensors):
+    """(N,C,H,W) tensor -> (N,H,W,C) numpy (models/basic.py:10-12).  Host I/O helper."""
+    return np.transpose(tensors.detach().to("cpu").numpy(), (0, 2, 3, 1))
+
+
+def _ctx(t):
+    if t.device.type != "cuda":
+        raise _lib.DiscoError("disentangledcolorization_b200.basic runs on a CUDA (B200) device only")
+    handle = _lib.Handle.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return handle, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _pool(feat, prob, sp_h, sp_w):
+    if sp_h != 16 or sp_w != 16:
+        raise _lib.DiscoError("only 16x16 super-pixels are built")
+    B, Cc, H, W = feat.shape
+    if Cc > 66:
+        raise _lib.DiscoError("poolfeat: at most 64 feature + 2 colour channels")
+    handle, stream = _ctx(feat)
+    dev = feat.device
+    h, w = H // 16, W // 16
+    f32 = dict(dtype=torch.float32, device=dev)
+    # split into the (<=64 feature, 2 colour) layout of the fused kernel; pad features with zeros
+    nf = min(Cc, 64)
+    feats = torch.zeros(B, H, W, 64, **f32)
+    feats[..., :nf] = feat[:, :nf].permute(0, 2, 3, 1)
+    ab = None
+    if Cc > 64:
+        ab = torch.zeros(B, 2, H, W, **f32)
+        ab[:, :Cc - 64] = feat[:, 64:]
+    partial = torch.empty(B, h, w, 9, 68, **f32)
+    tokens, spix = torch.empty(B, h * w, 64, **f32), torch.empty(B, 2, h, w, **f32)
+    conf, sizes = torch.empty(B, h * w, **f32), torch.empty(B, h * w, **f32)
+    _lib.check(handle.lib.disco_poolfeat(handle.h, _lib.F32, _p(feats), _p(ab), _p(prob.float().contiguous()), B, H, W,
+                                         64, _p(partial), _p(tokens), _p(spix), _p(conf), _p(sizes), stream),
+               "disco_poolfeat")
+    pooled = tokens.view(B, h, w, 64).permute(0, 3, 1, 2)[:, :nf]
+    if Cc > 64:
+        pooled = torch.cat([pooled, spix[:, :Cc - 64]], 1)
+    return pooled.contiguous(), conf.view(B, 1, h, w), sizes.view(B, 1, h, w)
+
+
+def poolfeat(input, prob, sp_h=2, sp_w=2, need_entry_prob=False):
+    """models/basic.py:274-324."""
+    pooled, conf, _ = _pool(input.float(), prob, sp_h, sp_w)
+    return (pooled, conf) if need_entry_prob else pooled
+
+
+def get_spixel_size(affinity_map, sp_h=2, sp_w=2, elem_thres=25):
+    """models/basic.py:327-335."""
+    ones = torch.ones(affinity_map.shape[0], 1, *affinity_map.shape[2:], device=affinity_map.device)
+    return _pool(ones, affinity_map, sp_h, sp_w)[2]
+
+
+def upfeat(input, prob, up_h=2, up_w=2):
+    """models/basic.py:338-376: (B,C,h,w) tokens + (B,9,H,W) affinity -> (B,C,H,W), C <= 64."""
+    if up_h != 16 or up_w != 16:
+        raise _lib.DiscoError("only 16x16 super-pixels are built")
+    B, Cc, h, w = input.shape
+    if Cc > 64:
+        raise _lib.DiscoError("upfeat: at most 64 channels")
+    handle, stream = _ctx(input)
+    H, W = h * 16, w * 16
+    tok = torch.zeros(B, h * w, 64, dtype=torch.float32, device=input.device)
+    tok[..., :Cc] = input.float().flatten(2).transpose(1, 2)
+    out = torch.empty(B, H, W, 64, dtype=torch.float32, device=input.device)
+    _lib.check(handle.lib.disco_upfeat(handle.h, _lib.F32, _p(tok), _p(prob.float().contiguous()), B, H, W, 64, _p(out),
+                                       stream), "disco_upfeat")
+    return out[..., :Cc].permute(0, 3, 1, 2).contiguous()
+
+
+class ColorLabel:
+    """models/basic.py:149-218 (the parts on the inference path)."""
+
+    def __init__(self, lambda_=0.5, device="cuda"):
+        self.q_to_ab = torch.from_numpy(Q_TO_AB.copy()).to(device)
+
+    def decode_ind2ab(self, batch_q, T=0.38):
+        """T-th most probable bin -> ab/110 (integer T) or annealed mean (fractional T); host-side glue on
+        (N,313,h,w) logits whose result the reference CLI discards (inference.py:114-115)."""
+        q = torch.softmax(batch_q, dim=1)
+        table = self.q_to_ab.to(q.device)
+        if T % 1 == 0:
+            idx = torch.sort(q, dim=1, descending=True)[1][:, int(T)]
+            ab = table[idx].permute(0, 3, 1, 2)
+        else:
+            q = torch.exp(q / T)
+            q = q / q.sum(dim=1, keepdim=True)
+            ab = torch.einsum("nqhw,qc->nchw", q, table)
+        return (ab / 110.0).type(batch_q.dtype)
+
+    def encode_ab2ind_hard(self, batch_ab):
+        """argmax of encode_ab2ind (models/basic.py:177-194 + models/model.py:120,166) == nearest bin."""
+        B, _, h, w = batch_ab.shape
+        handle, stream = _ctx(batch_ab)
+        labels = torch.empty(B * h * w, dtype=torch.int32, device=batch_ab.device)
+        _lib.check(handle.lib.disco_token_labels(handle.h, 1, _p(batch_ab.float().contiguous()),
+                                                 _p(self.q_to_ab.to(batch_ab.device)), B, h * w, _p(labels), None,
+                                                 stream), "disco_token_labels")
+        return labels.view(B, 1, h, w).long()

@@ -1,0 +1,57 @@
+// Shared host/device helpers for libdisco_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/disco_b200.h"
+
+struct disco_handle {
+  int device;
+  int sm_count;
+  int64_t launches;
+  void* tmap_encode;   // cuTensorMapEncodeTiled entry point (resolved lazily)
+};
+
+void disco_set_error(const char* fmt, ...);
+
+#define DISCO_CHECK_ARG(cond, ...)                 \
+  do {                                             \
+    if (!(cond)) {                                 \
+      disco_set_error(__VA_ARGS__);                \
+      return DISCO_ERR_INVALID;                    \
+    }                                              \
+  } while (0)
+
+#define DISCO_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      disco_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return DISCO_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+
+#define DISCO_LAUNCH_CHECK(h)                      \
+  do {                                             \
+    (h)->launches++;                               \
+    DISCO_CUDA(cudaGetLastError());                \
+  } while (0)
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == DISCO_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == DISCO_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// internal entry points implemented in the individual .cu files
+int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
+int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
+bool conv_tc_supported(const disco_conv_desc* d);

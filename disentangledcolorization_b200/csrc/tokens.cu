@@ -1,0 +1,372 @@
+// Token path: linear layers with fused epilogues, attention core, batched k-means anchor selection,
+// token labels.  Everything is fp32 (the token path is 0.2 % of the FLOPs and feeds discrete
+// decisions -- k-means assignments, argmax labels -- so it is kept in full precision).
+#include "common.cuh"
+#include <cfloat>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// linear: 64x64 output tile per CTA, K stepped by 16, 4x4 register micro-tiles
+// ------------------------------------------------------------------------------------------
+constexpr int LT = 64;
+constexpr int LK = 16;
+
+__global__ void __launch_bounds__(256) linear_kernel(const disco_linear_desc d) {
+  __shared__ float As[LK][LT + 4];
+  __shared__ float Bs[LK][LT + 4];
+  __shared__ float Cs[LT][LT + 1];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * LT, n0 = blockIdx.y * LT;
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool use_pos = d.pos != nullptr && n0 < d.pos_cols;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2, lc = (tid & 3) * 4;   // load role: row lr, k offset lc..lc+3
+  for (int k0 = 0; k0 < d.K; k0 += LK) {
+    {
+      const int row = m0 + lr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < d.M) {
+        v = *reinterpret_cast<const float4*>(d.X + (size_t)row * d.K + k0 + lc);
+        if (use_pos) {
+          const float4 p = *reinterpret_cast<const float4*>(d.pos + (size_t)(row % d.S) * d.K + k0 + lc);
+          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+      }
+      As[lc + 0][lr] = v.x; As[lc + 1][lr] = v.y; As[lc + 2][lr] = v.z; As[lc + 3][lr] = v.w;
+      const int col = n0 + lr;
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < d.N) wv = *reinterpret_cast<const float4*>(d.W + (size_t)col * d.K + k0 + lc);
+      Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      float v = acc[i][j];
+      if (row < d.M && col < d.N) {
+        if (d.b) v += d.b[col];
+        if (col < d.scale_cols) v *= d.col_scale;
+        if (d.hint_mask) {
+          const float m = d.hint_mask[row];
+          if (m != 0.f) v += m * (d.emb[(size_t)d.labels[row] * d.N + col] + d.emb[(size_t)313 * d.N + col]);
+        }
+        if (d.relu) v = v > 0.f ? v : 0.f;
+        if (d.residual) v += d.residual[(size_t)row * d.N + col];
+      }
+      Cs[ty * 4 + i][tx * 4 + j] = v;
+    }
+  }
+  __syncthreads();
+  if (d.ln_gamma) {   // N == 64: the whole row lives in this tile
+    if (tid < LT) {
+      float mean = 0.f;
+      for (int c = 0; c < 64; ++c) mean += Cs[tid][c];
+      mean *= (1.f / 64.f);
+      float var = 0.f;
+      for (int c = 0; c < 64; ++c) { const float t = Cs[tid][c] - mean; var = fmaf(t, t, var); }
+      var *= (1.f / 64.f);
+      const float rstd = 1.0f / sqrtf(var + 1e-5f);
+      for (int c = 0; c < 64; ++c) Cs[tid][c] = (Cs[tid][c] - mean) * rstd * d.ln_gamma[c] + d.ln_beta[c];
+    }
+    __syncthreads();
+  }
+  if (d.transpose_S > 0) {
+    // Y[(row / S)][col][row % S]; consecutive threads -> consecutive rows (contiguous in memory)
+    for (int e = tid; e < LT * LT; e += 256) {
+      const int c = e >> 6, r = e & 63;
+      const int row = m0 + r, col = n0 + c;
+      if (row < d.M && col < d.N)
+        d.Y[((size_t)(row / d.transpose_S) * d.N + col) * d.transpose_S + row % d.transpose_S] = Cs[r][c];
+    }
+  } else {
+    for (int e = tid; e < LT * LT; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      const int row = m0 + r, col = n0 + c;
+      if (row < d.M && col < d.N) d.Y[(size_t)row * d.N + col] = Cs[r][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention core: grid (B*8, ceil(S/128)), 128 threads, thread = query; K/V of the head in smem
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ out) {
+  extern __shared__ float kv[];   // K [S][8] then V [S][8]
+  float* Ks = kv;
+  float* Vs = kv + (size_t)S * 8;
+  const int n = blockIdx.x >> 3, hd = blockIdx.x & 7;
+  const float* base = qkv + (size_t)n * S * 192;
+  for (int e = threadIdx.x; e < S * 2; e += 128) {
+    const int t = e >> 1, half = e & 1;
+    const float4 k4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 64 + hd * 8 + half * 4);
+    const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 128 + hd * 8 + half * 4);
+    *reinterpret_cast<float4*>(Ks + t * 8 + half * 4) = k4;
+    *reinterpret_cast<float4*>(Vs + t * 8 + half * 4) = v4;
+  }
+  __syncthreads();
+  const int qi = blockIdx.y * 128 + threadIdx.x;
+  if (qi >= S) return;
+  float q[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8);
+    const float4 b = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8 + 4);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+  }
+  float mx = -FLT_MAX;
+  for (int j = 0; j < S; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(Ks + j * 8);
+    const float4 b = *reinterpret_cast<const float4*>(Ks + j * 8 + 4);
+    float s = q[0] * a.x;
+    s = fmaf(q[1], a.y, s); s = fmaf(q[2], a.z, s); s = fmaf(q[3], a.w, s);
+    s = fmaf(q[4], b.x, s); s = fmaf(q[5], b.y, s); s = fmaf(q[6], b.z, s); s = fmaf(q[7], b.w, s);
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < S; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(Ks + j * 8);
+    const float4 b = *reinterpret_cast<const float4*>(Ks + j * 8 + 4);
+    float s = q[0] * a.x;
+    s = fmaf(q[1], a.y, s); s = fmaf(q[2], a.z, s); s = fmaf(q[3], a.w, s);
+    s = fmaf(q[4], b.x, s); s = fmaf(q[5], b.y, s); s = fmaf(q[6], b.z, s); s = fmaf(q[7], b.w, s);
+    const float e = expf(s - mx);
+    sum += e;
+    const float4 va = *reinterpret_cast<const float4*>(Vs + j * 8);
+    const float4 vb = *reinterpret_cast<const float4*>(Vs + j * 8 + 4);
+    o[0] = fmaf(e, va.x, o[0]); o[1] = fmaf(e, va.y, o[1]); o[2] = fmaf(e, va.z, o[2]); o[3] = fmaf(e, va.w, o[3]);
+    o[4] = fmaf(e, vb.x, o[4]); o[5] = fmaf(e, vb.y, o[5]); o[6] = fmaf(e, vb.z, o[6]); o[7] = fmaf(e, vb.w, o[7]);
+  }
+  const float inv = 1.0f / sum;
+  float* dst = out + ((size_t)n * S + qi) * 64 + hd * 8;
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+}
+
+// ------------------------------------------------------------------------------------------
+// k-means (Lloyd) + anchor pick, one CTA per image.  KMAX clusters, D = 64.
+// ------------------------------------------------------------------------------------------
+constexpr int KMAX = 32;
+constexpr int KD = 64;
+
+struct KmArgs {
+  const float* X; const int32_t* init_idx; const int32_t* draws; int n_draws;
+  const float* sizes; int B, S, K, iter_limit; float tol;
+  int32_t* assign; float* hint_mask; int32_t* events; int32_t* iters;
+};
+
+// Runs one image.  Returns (through smem scalars) the number of draws consumed.
+__device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float* C, float* Cprev, int* cnt,
+                                 int* ridx, float* shiftk, int* s_flag) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int S = a.S, K = a.K;
+  const float* X = a.X + (size_t)n * S * KD;
+  int32_t* assign = a.assign + (size_t)n * S;
+  for (int e = tid; e < K * KD; e += nt) C[e] = X[(size_t)a.init_idx[n * K + e / KD] * KD + (e % KD)];
+  if (tid == 0) { s_flag[0] = 0; /* events */ s_flag[1] = 0; /* stop */ s_flag[2] = 0; /* iterations */ }
+  __syncthreads();
+  while (true) {
+    // 1. assignment (first minimum wins, like torch.argmin)
+    for (int t = tid; t < S; t += nt) {
+      const float* x = X + (size_t)t * KD;
+      float best = FLT_MAX; int bi = 0;
+      for (int k = 0; k < K; ++k) {
+        float dsum = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < KD; ++c) { const float df = x[c] - C[k * KD + c]; dsum = fmaf(df, df, dsum); }
+        if (dsum < best) { best = dsum; bi = k; }
+      }
+      assign[t] = bi;
+    }
+    for (int e = tid; e < K * KD; e += nt) Cprev[e] = C[e];
+    __syncthreads();
+    // 2. member counts, then draws for empty clusters in cluster order (reference: clusterkit.py:178-184)
+    for (int k = tid; k < K; k += nt) {
+      int c = 0;
+      for (int t = 0; t < S; ++t) c += (assign[t] == k);
+      cnt[k] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < K; ++k) {
+        ridx[k] = -1;
+        if (cnt[k] == 0) {
+          const int di = draw_offset + s_flag[0];
+          if (di < a.n_draws) ridx[k] = a.draws[di]; else { ridx[k] = 0; a.events[a.B + 1] = 1; }
+          s_flag[0]++;
+        }
+      }
+    }
+    __syncthreads();
+    // 3. centre update: mean of members in token order
+    for (int e = tid; e < K * KD; e += nt) {
+      const int k = e / KD, c = e % KD;
+      float v;
+      if (cnt[k] == 0) {
+        v = X[(size_t)ridx[k] * KD + c];
+      } else {
+        float s = 0.f;
+        for (int t = 0; t < S; ++t) if (assign[t] == k) s += X[(size_t)t * KD + c];
+        v = s / (float)cnt[k];
+      }
+      C[e] = v;
+    }
+    __syncthreads();
+    // 4. centre shift = sum_k ||c_k - c_k_prev||
+    for (int k = tid; k < K; k += nt) {
+      float s = 0.f;
+      for (int c = 0; c < KD; ++c) { const float df = C[k * KD + c] - Cprev[k * KD + c]; s = fmaf(df, df, s); }
+      shiftk[k] = sqrtf(s);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float sh = 0.f;
+      for (int k = 0; k < K; ++k) sh += shiftk[k];
+      s_flag[2]++;
+      s_flag[1] = (sh * sh < a.tol) || (a.iter_limit != 0 && s_flag[2] >= a.iter_limit);
+    }
+    __syncthreads();
+    if (s_flag[1]) break;
+  }
+  // anchor pick: per cluster the member with the largest super-pixel (first maximum), anchor_gen.py:98-101
+  float* hint = a.hint_mask + (size_t)n * S;
+  for (int t = tid; t < S; t += nt) hint[t] = 0.f;
+  __syncthreads();
+  for (int k = tid; k < K; k += nt) {
+    float best = -FLT_MAX; int bi = 0;
+    for (int t = 0; t < S; ++t) {
+      const float sc = (assign[t] == k ? 1.0f : 0.0f) + a.sizes[(size_t)n * S + t] * 0.01f;
+      if (sc > best) { best = sc; bi = t; }
+    }
+    ridx[k] = bi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < K; ++k) hint[ridx[k]] += 1.0f;
+    a.events[n] = s_flag[0];
+    a.iters[n] = s_flag[2];
+  }
+  __syncthreads();
+}
+
+// mode 0: grid B, speculative (draw offset 0).  mode 1: grid 1, sequential fix-up in image order.
+__global__ void __launch_bounds__(256) kmeans_anchor_kernel(const KmArgs a, int mode) {
+  __shared__ float C[KMAX * KD];
+  __shared__ float Cprev[KMAX * KD];
+  __shared__ int cnt[KMAX];
+  __shared__ int ridx[KMAX];
+  __shared__ float shiftk[KMAX];
+  __shared__ int s_flag[4];
+  if (mode == 0) {
+    kmeans_one_image(a, blockIdx.x, 0, C, Cprev, cnt, ridx, shiftk, s_flag);
+  } else {
+    int running = 0;
+    for (int n = 0; n < a.B; ++n) {
+      const int ev = a.events[n];
+      if (ev > 0 && running > 0) kmeans_one_image(a, n, running, C, Cprev, cnt, ridx, shiftk, s_flag);
+      __syncthreads();
+      running += a.events[n];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.events[a.B] = running;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// labels: one thread per token; logits are read in the API layout [B,313,S] (coalesced over tokens)
+// ------------------------------------------------------------------------------------------
+__global__ void token_labels_kernel(int mode, const float* __restrict__ src, const float* __restrict__ table, int B,
+                                    int S, int32_t* __restrict__ labels, float* __restrict__ colors) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S) return;
+  const int n = idx / S, t = idx % S;
+  int bi = 0;
+  if (mode == 0) {
+    float best = -FLT_MAX;
+    const float* col = src + (size_t)n * 313 * S + t;
+    for (int c = 0; c < 313; ++c) { const float v = col[(size_t)c * S]; if (v > best) { best = v; bi = c; } }
+  } else {
+    float best = FLT_MAX;
+    const float a0 = src[((size_t)n * 2 + 0) * S + t] * 110.0f, a1 = src[((size_t)n * 2 + 1) * S + t] * 110.0f;
+    for (int c = 0; c < 313; ++c) {
+      const float d0 = table[c * 2] - a0, d1 = table[c * 2 + 1] - a1;
+      const float v = sqrtf(d0 * d0 + d1 * d1);
+      if (v < best) { best = v; bi = c; }
+    }
+  }
+  labels[idx] = bi;
+  if (colors && mode == 0) {
+    colors[((size_t)n * 2 + 0) * S + t] = table[bi * 2] / 110.0f;
+    colors[((size_t)n * 2 + 1) * S + t] = table[bi * 2 + 1] / 110.0f;
+  }
+}
+
+}  // namespace
+
+extern "C" int disco_linear(disco_handle* h, const disco_linear_desc* d, void* stream) {
+  DISCO_CHECK_ARG(h && d && d->X && d->W && d->Y, "linear: null pointer");
+  DISCO_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->K % 16 == 0, "linear: K must be a positive multiple of 16 (got %d)", d->K);
+  DISCO_CHECK_ARG(!d->ln_gamma || d->N == 64, "linear: LayerNorm epilogue needs N == 64");
+  DISCO_CHECK_ARG(!d->pos || (d->S > 0 && d->pos_cols % 64 == 0), "linear: pos needs S > 0 and pos_cols %% 64 == 0");
+  DISCO_CHECK_ARG(!d->hint_mask || (d->labels && d->emb), "linear: hint embedding needs labels and emb");
+  dim3 grid((d->M + LT - 1) / LT, (d->N + LT - 1) / LT);
+  linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}
+
+extern "C" int disco_attention(disco_handle* h, const float* qkv, int batch, int S, float* out, void* stream) {
+  DISCO_CHECK_ARG(h && qkv && out && batch > 0 && S > 0, "attention: bad argument");
+  const size_t smem = (size_t)S * 16 * sizeof(float);
+  DISCO_CHECK_ARG(smem <= 200 * 1024, "attention: S=%d too large for the shared-memory K/V stage", S);
+  if (smem > 48 * 1024)
+    DISCO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(batch * 8, (S + 127) / 128);
+  attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, S, out);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}
+
+extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_t* init_idx, const int32_t* draws,
+                                   int n_draws, const float* sizes, int batch, int S, int K, int iter_limit, float tol,
+                                   int32_t* assign, float* hint_mask, int32_t* events, int32_t* iters, void* stream) {
+  DISCO_CHECK_ARG(h && X && init_idx && draws && sizes && assign && hint_mask && events && iters, "kmeans: null pointer");
+  DISCO_CHECK_ARG(K >= 1 && K <= KMAX, "kmeans: K must be in [1,%d] (got %d)", KMAX, K);
+  DISCO_CHECK_ARG(K <= S, "kmeans: n_clusters (%d) exceeds the number of tokens (%d)", K, S);
+  KmArgs a{X, init_idx, draws, n_draws, sizes, batch, S, K, iter_limit, tol, assign, hint_mask, events, iters};
+  cudaStream_t st = (cudaStream_t)stream;
+  DISCO_CUDA(cudaMemsetAsync(events, 0, sizeof(int32_t) * (batch + 2), st));
+  kmeans_anchor_kernel<<<batch, 256, 0, st>>>(a, 0);
+  DISCO_LAUNCH_CHECK(h);
+  kmeans_anchor_kernel<<<1, 256, 0, st>>>(a, 1);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}
+
+extern "C" int disco_token_labels(disco_handle* h, int mode, const float* src, const float* q_to_ab, int batch, int S,
+                                  int32_t* labels, float* colors, void* stream) {
+  DISCO_CHECK_ARG(h && src && q_to_ab && labels, "token_labels: null pointer");
+  DISCO_CHECK_ARG(mode == 0 || mode == 1, "token_labels: mode must be 0 or 1");
+  token_labels_kernel<<<(batch * S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mode, src, q_to_ab, batch, S, labels, colors);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}

@@ -1,0 +1,337 @@
+"""Host-side executor of the DISCO forward on the CUDA library (one Engine per model instance).
+
+Responsibilities (plumbing only -- all arithmetic on the path runs in libdisco_b200.so):
+  * fold + pack the reference-schema state_dict into device tensors (netspec.fold);
+  * own the activation workspace for each (batch, H, W) it has seen;
+  * issue the launch plan of `AnchorColorProb.forward` (reference models/model.py:103-199,
+    test_mode branch) on the caller's current CUDA stream;
+  * reproduce the reference's host RNG consumption: `np.random.choice(S, K, replace=False)` once per
+    image in batch order (clusterkit.py:107) and one `torch.randint(S, (1,))` per empty cluster
+    (clusterkit.py:182).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, netspec
+from .cielab import Q_TO_AB
+
+_DT = {"fp32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16)}
+_ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "lrelu": _lib.ACT_LRELU}
+_HEAD = {None: _lib.HEAD_NONE, "softmax9": _lib.HEAD_SOFTMAX9, "tanh2": _lib.HEAD_TANH2}
+N_DRAWS = 4096
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def position_table(h, w, device):
+    """PositionEmbeddingSine(32, normalize=True) as an (S, 64) table (models/position_encoding.py:26-47).
+    Input-independent: computed once per grid size on the host and cached on the device."""
+    ones = torch.ones(h, w)
+    y = ones.cumsum(0, dtype=torch.float32)
+    x = ones.cumsum(1, dtype=torch.float32)
+    y = y / (y[-1:, :] + 1e-6) * (2 * math.pi)
+    x = x / (x[:, -1:] + 1e-6) * (2 * math.pi)
+    d = torch.arange(32, dtype=torch.float32)
+    d = 10000.0 ** (2 * torch.div(d, 2, rounding_mode="floor") / 32)
+    px, py = x[:, :, None] / d, y[:, :, None] / d
+    px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), dim=3).flatten(2)
+    py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((py, px), dim=2).reshape(h * w, 64).contiguous().to(device)
+
+
+class _PackedConv:
+    """Device-resident folded parameters of one fused conv op."""
+
+    def __init__(self, folded, device):
+        op = folded.op
+        blocks, offs, off = [], [], 0
+        for w in folded.weights:
+            if op.kind == "deconv4":
+                blk = w.permute(2, 3, 0, 1).reshape(16, w.shape[0], w.shape[1])   # [tap][cin][cout]
+            else:
+                blk = w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0])
+            offs.append(off)
+            off += blk.numel()
+            blocks.append(blk.reshape(-1))
+        self.op = op
+        self.w32 = torch.cat(blocks).contiguous().to(device)
+        self.w_off = offs
+        self.bias = folded.bias.to(device)
+        self.post_scale = folded.post_scale.to(device) if folded.post_scale is not None else None
+        self.post_shift = folded.post_shift.to(device) if folded.post_shift is not None else None
+
+
+class Engine:
+    def __init__(self, state_dict, device, precision="bf16", n_clusters=8, sp_size=16, enhanced=True):
+        if precision not in _DT:
+            raise ValueError(f"precision must be one of {list(_DT)}")
+        if sp_size != 16:
+            raise _lib.DiscoError("only sp_size=16 is built (all BASELINE configs); got %d" % sp_size)
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.DiscoError("disentangledcolorization_b200 runs on a CUDA (B200) device only; "
+                                  "there is no CPU path -- move the model with .cuda()")
+        self.device = device
+        self.handle = _lib.Handle.get(device.index if device.index is not None else torch.cuda.current_device())
+        self.lib = self.handle.lib
+        self.precision = precision
+        self.dt_code, self.dt_torch = _DT[precision]
+        self.n_clusters = n_clusters
+        self.enhanced = enhanced
+        self._ws = {}
+        self._pos = {}
+        self._pending_rng = None
+        self.last_kmeans_iters = None
+        self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd):
+        sd = {k: v.detach().to("cpu") for k, v in sd.items()}
+        dev = self.device
+        groups = [("segnet", netspec.segnet_ops()), ("repnet", netspec.repnet_ops())]
+        if self.enhanced:
+            groups.append(("enhanceNet", netspec.enhancenet_ops()))
+        self.convs = {name: [_PackedConv(netspec.fold(sd, op), dev) for op in ops] for name, ops in groups}
+        f = lambda k: sd[k].float().contiguous().to(dev)
+        self.stacks = {}
+        for stack in ("wildpath", "hintpath"):
+            layers = []
+            for i in range(netspec.N_LAYERS):
+                p = f"{stack}.layers.{i}."
+                layers.append(dict(in_w=f(p + "self_attn.in_proj_weight"), in_b=f(p + "self_attn.in_proj_bias"),
+                                   out_w=f(p + "self_attn.out_proj.weight"), out_b=f(p + "self_attn.out_proj.bias"),
+                                   l1_w=f(p + "linear1.weight"), l1_b=f(p + "linear1.bias"),
+                                   l2_w=f(p + "linear2.weight"), l2_b=f(p + "linear2.bias"),
+                                   n1_w=f(p + "norm1.weight"), n1_b=f(p + "norm1.bias"),
+                                   n2_w=f(p + "norm2.weight"), n2_b=f(p + "norm2.bias")))
+            self.stacks[stack] = layers
+        self.mid_w = f("mid_word_prj.weight")
+        self.trg_w = f("trg_word_prj.weight")
+        emb = sd["trg_word_emb.weight"].float()
+        self.emb_src = emb[:, :64].contiguous().to(dev)                 # (64, 64): acts on the token features
+        self.emb_tab = emb[:, 64:].t().contiguous().to(dev)             # (314, 64): 313 label columns + mask column
+        self.q_to_ab = torch.from_numpy(Q_TO_AB.copy()).to(dev)
+        self._ws.clear()
+
+    # ------------------------------------------------------------------ workspace / plan
+    def _workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        if H % 16 or W % 16 or H <= 0 or W <= 0:
+            raise _lib.DiscoError(f"H and W must be positive multiples of 16 (got {H}x{W}); the reference has the "
+                                  "same constraint (SpixelNet has four stride-2 stages)")
+        dev = self.device
+        h, w = H // 16, W // 16
+        S = h * w
+        if self.n_clusters > S:
+            raise _lib.DiscoError(f"n_clusters={self.n_clusters} exceeds the {S} super-pixel tokens of a {H}x{W} image")
+        bufs = {}
+        plans = {}
+        f32 = dict(dtype=torch.float32, device=dev)
+        for net, packed in self.convs.items():
+            descs = []
+            for pc in packed:
+                op = pc.op
+                Ho, Wo = H // op.scale, W // op.scale
+                if op.head == "softmax9":
+                    out = torch.empty(B, 9, Ho, Wo, **f32)
+                elif op.head == "tanh2":
+                    out = torch.empty(B, 2, Ho, Wo, **f32)
+                else:
+                    out = torch.empty(B, Ho, Wo, op.cout, dtype=self.dt_torch, device=dev)
+                bufs[op.out] = out
+                descs.append((pc, Ho, Wo))
+            plans[net] = descs
+        bufs["full_feats"] = torch.empty(B, H, W, 64, dtype=self.dt_torch, device=dev)
+        M = B * S
+        tok = dict(partial=torch.empty(B, h, w, 9, 68, **f32), tokens=torch.empty(B, S, 64, **f32),
+                   spix_ab=torch.empty(B, 2, h, w, **f32), conf=torch.empty(B, S, **f32),
+                   sizes=torch.empty(B, S, **f32), qkv=torch.empty(M, 192, **f32), att=torch.empty(M, 64, **f32),
+                   x1=torch.empty(M, 64, **f32), hid=torch.empty(M, 256, **f32), xa=torch.empty(M, 64, **f32),
+                   xb=torch.empty(M, 64, **f32), enc=torch.empty(M, 64, **f32), dec=torch.empty(M, 64, **f32),
+                   hint_seq=torch.empty(M, 64, **f32), labels=torch.empty(M, dtype=torch.int32, device=dev),
+                   assign=torch.empty(M, dtype=torch.int32, device=dev),
+                   events=torch.zeros(B + 2, dtype=torch.int32, device=dev),
+                   iters=torch.zeros(B, dtype=torch.int32, device=dev),
+                   init_idx=torch.empty(B, self.n_clusters, dtype=torch.int32, device=dev),
+                   draws=torch.zeros(N_DRAWS, dtype=torch.int32, device=dev),
+                   init_idx_host=torch.empty(B, self.n_clusters, dtype=torch.int32).pin_memory(),
+                   draws_host=torch.empty(N_DRAWS, dtype=torch.int32).pin_memory(),
+                   events_host=torch.zeros(B + 2, dtype=torch.int32).pin_memory())
+        if (h, w) not in self._pos:
+            self._pos[(h, w)] = position_table(h, w, dev)
+        ws = dict(bufs=bufs, plans=plans, tok=tok, h=h, w=w, S=S, descs={})
+        self._ws[key] = ws
+        return ws
+
+    def _conv_desc(self, ws, pc, Ho, Wo, B, bufs):
+        op = pc.op
+        d = _lib.ConvDesc()
+        d.kind = _lib.DECONV4 if op.kind == "deconv4" else _lib.CONV3
+        d.stride, d.dtype = op.stride, self.dt_code
+        d.batch, d.Ho, d.Wo, d.Cout = B, Ho, Wo, op.cout
+        d.n_src = len(op.srcs)
+        for i, s in enumerate(op.srcs):
+            t = bufs[s.buf]
+            if s.buf == "gray":                     # (B,1,H,W) fp32 == NHWC with C = 1
+                Hs, Ws, Cs, is32 = t.shape[2], t.shape[3], 1, 1
+            else:
+                Hs, Ws, Cs, is32 = t.shape[1], t.shape[2], t.shape[3], 0
+            d.src[i].ptr = t.data_ptr()
+            d.src[i].H, d.src[i].W, d.src[i].C = Hs, Ws, Cs
+            d.src[i].up2, d.src[i].is_f32, d.src[i].w_off = int(s.up2), is32, pc.w_off[i]
+        d.weights, d.bias = pc.w32.data_ptr(), pc.bias.data_ptr()
+        d.post_scale = pc.post_scale.data_ptr() if pc.post_scale is not None else None
+        d.post_shift = pc.post_shift.data_ptr() if pc.post_shift is not None else None
+        d.residual = bufs[op.res].data_ptr() if op.res else None
+        d.act, d.slope, d.head = _ACT[op.act], op.slope, _HEAD[op.head]
+        d.out = bufs[op.out].data_ptr()
+        return d
+
+    def _run_net(self, net, ws, B, gray, stream):
+        bufs = ws["bufs"]
+        bufs["gray"] = gray
+        key = (net, gray.data_ptr())
+        descs = ws["descs"].get(key)
+        if descs is None:
+            descs = [self._conv_desc(ws, pc, Ho, Wo, B, bufs) for pc, Ho, Wo in ws["plans"][net]]
+            ws["descs"] = {k: v for k, v in ws["descs"].items() if k[0] != net}
+            ws["descs"][key] = descs
+        for d in descs:
+            _lib.check(self.lib.disco_conv(self.handle.h, C.byref(d), stream), "disco_conv")
+
+    # ------------------------------------------------------------------ token path
+    def _linear(self, stream, X, W, Y, b=None, pos=None, pos_cols=0, S=0, col_scale=1.0, scale_cols=0, relu=False,
+                residual=None, ln=None, hint=None, transpose_S=0):
+        d = _lib.LinearDesc()
+        d.X, d.W, d.b = X.data_ptr(), W.data_ptr(), (b.data_ptr() if b is not None else None)
+        d.M, d.N, d.K = X.shape[0], W.shape[0], W.shape[1]
+        d.pos, d.pos_cols, d.S = (pos.data_ptr() if pos is not None else None), pos_cols, S
+        d.col_scale, d.scale_cols, d.relu = col_scale, scale_cols, int(relu)
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.ln_gamma, d.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (None, None)
+        if hint is not None:
+            d.hint_mask, d.labels, d.emb = hint[0].data_ptr(), hint[1].data_ptr(), hint[2].data_ptr()
+        d.transpose_S, d.Y = transpose_S, Y.data_ptr()
+        _lib.check(self.lib.disco_linear(self.handle.h, C.byref(d), stream), "disco_linear")
+
+    def _encoder_stack(self, stack, x_in, out, ws, B, stream):
+        """TransformerEncoder(use_dense_pos=True), 6 post-norm layers (models/transformer2d.py:17-28,52-60)."""
+        tok, S = ws["tok"], ws["S"]
+        pos = self._pos[(ws["h"], ws["w"])]
+        x = x_in
+        layers = self.stacks[stack]
+        for i, L in enumerate(layers):
+            self._linear(stream, x, L["in_w"], tok["qkv"], b=L["in_b"], pos=pos, pos_cols=128, S=S,
+                         col_scale=8 ** -0.5, scale_cols=64)
+            _lib.check(self.lib.disco_attention(self.handle.h, _ptr(tok["qkv"]), B, S, _ptr(tok["att"]), stream),
+                       "disco_attention")
+            self._linear(stream, tok["att"], L["out_w"], tok["x1"], b=L["out_b"], residual=x, ln=(L["n1_w"], L["n1_b"]))
+            self._linear(stream, tok["x1"], L["l1_w"], tok["hid"], b=L["l1_b"], relu=True)
+            y = out if i == len(layers) - 1 else (tok["xa"] if i % 2 == 0 else tok["xb"])
+            self._linear(stream, tok["hid"], L["l2_w"], y, b=L["l2_b"], residual=tok["x1"], ln=(L["n2_w"], L["n2_b"]))
+            x = y
+
+    # ------------------------------------------------------------------ RNG protocol
+    def _resolve_rng(self):
+        """Advance torch's CPU generator by the number of empty-cluster draws the last forward consumed."""
+        pend = self._pending_rng
+        if pend is None:
+            return
+        self._pending_rng = None
+        state, events_host, event, S = pend
+        event.synchronize()
+        if int(events_host[-1]) != 0:
+            raise _lib.DiscoError("k-means consumed more than %d empty-cluster draws" % N_DRAWS)
+        used = int(events_host[-2])
+        torch.set_rng_state(state)
+        if used:
+            torch.randint(S, (used,))
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, gray, ab, sampled_T=0, hint_mask=None, sync_rng=True):
+        """Returns the reference 6-tuple (pal_logit, ref_logit, pred_colors, affinity_map, spix_colors, hint_mask)."""
+        self._resolve_rng()
+        if gray.dim() != 4 or gray.shape[1] != 1:
+            raise _lib.DiscoError(f"input_grays must be (N,1,H,W), got {tuple(gray.shape)}")
+        if sampled_T > 0:
+            raise _lib.DiscoError("sampled_T > 0 (--diverse) is not built yet")
+        B, _, H, W = gray.shape
+        if B == 0:
+            raise _lib.DiscoError("empty batch")
+        dev = self.device
+        gray = gray.to(device=dev, dtype=torch.float32).contiguous()
+        ab = ab.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(ab.shape) != (B, 2, H, W):
+            raise _lib.DiscoError(f"input_colors must be ({B},2,{H},{W}), got {tuple(ab.shape)}")
+        ws = self._workspace(B, H, W)
+        bufs, tok, S, h, w = ws["bufs"], ws["tok"], ws["S"], ws["h"], ws["w"]
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lib, hd = self.lib, self.handle.h
+        M = B * S
+
+        self._run_net("segnet", ws, B, gray, stream)                                   # model.py:104
+        self._run_net("repnet", ws, B, gray, stream)                                   # model.py:105
+        affinity = bufs["affinity"]
+        _lib.check(lib.disco_poolfeat(hd, self.dt_code, _ptr(bufs["pred_feats"]), _ptr(ab), _ptr(affinity), B, H, W, 64,
+                                      _ptr(tok["partial"]), _ptr(tok["tokens"]), _ptr(tok["spix_ab"]), _ptr(tok["conf"]),
+                                      _ptr(tok["sizes"]), stream), "disco_poolfeat")      # model.py:114-121
+        tokens = tok["tokens"].view(M, 64)
+        self._encoder_stack("wildpath", tokens, tok["enc"], ws, B, stream)              # model.py:133
+        pal_logit = torch.empty(B, 313, h, w, dtype=torch.float32, device=dev)
+        self._linear(stream, tok["enc"], self.mid_w, pal_logit, transpose_S=S)          # model.py:134-135
+
+        if hint_mask is None:                                                           # model.py:140-141
+            K = self.n_clusters
+            for n in range(B):
+                tok["init_idx_host"][n] = torch.from_numpy(np.random.choice(S, K, replace=False).astype(np.int32))
+            state = torch.get_rng_state()
+            tok["draws_host"].copy_(torch.randint(S, (N_DRAWS,)).to(torch.int32))
+            torch.set_rng_state(state)
+            tok["init_idx"].copy_(tok["init_idx_host"], non_blocking=True)
+            tok["draws"].copy_(tok["draws_host"], non_blocking=True)
+            hint = torch.empty(B, 1, h, w, dtype=torch.float32, device=dev)
+            _lib.check(lib.disco_kmeans_anchor(hd, _ptr(tok["enc"]), _ptr(tok["init_idx"]), _ptr(tok["draws"]), N_DRAWS,
+                                               _ptr(tok["sizes"]), B, S, K, 20, 1e-4, _ptr(tok["assign"]), _ptr(hint),
+                                               _ptr(tok["events"]), _ptr(tok["iters"]), stream), "disco_kmeans_anchor")
+            tok["events_host"].copy_(tok["events"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._pending_rng = (state, tok["events_host"], ev, S)
+        else:
+            hint = hint_mask.to(device=dev, dtype=torch.float32).reshape(B, 1, h, w).contiguous()
+
+        spix_colors = torch.empty(B, 2, h, w, dtype=torch.float32, device=dev)
+        if sampled_T < 0:                                                               # model.py:145-147,166
+            spix_colors.copy_(tok["spix_ab"])
+            _lib.check(lib.disco_token_labels(hd, 1, _ptr(tok["spix_ab"]), _ptr(self.q_to_ab), B, S, _ptr(tok["labels"]),
+                                              None, stream), "disco_token_labels")
+        else:                                                                           # model.py:161,166
+            _lib.check(lib.disco_token_labels(hd, 0, _ptr(pal_logit), _ptr(self.q_to_ab), B, S, _ptr(tok["labels"]),
+                                              _ptr(spix_colors), stream), "disco_token_labels")
+        self._linear(stream, tokens, self.emb_src, tok["hint_seq"],
+                     hint=(hint, tok["labels"], self.emb_tab))                          # model.py:175-185
+        self._encoder_stack("hintpath", tok["hint_seq"], tok["dec"], ws, B, stream)     # model.py:186
+        ref_logit = torch.empty(B, 313, h, w, dtype=torch.float32, device=dev)
+        self._linear(stream, tok["dec"], self.trg_w, ref_logit, transpose_S=S)          # model.py:187-189
+
+        pred = None
+        if self.enhanced:
+            _lib.check(lib.disco_upfeat(hd, self.dt_code, _ptr(tok["dec"]), _ptr(affinity), B, H, W, 64,
+                                        _ptr(bufs["full_feats"]), stream), "disco_upfeat")   # model.py:194-195
+            self._run_net("enhanceNet", ws, B, gray, stream)                            # model.py:196-197
+            pred = bufs["pred_colors"].clone()
+        if sync_rng:
+            self._resolve_rng()
+        return pal_logit, ref_logit, pred, affinity.clone(), spix_colors, hint
+
+    def kmeans_iterations(self, B, H, W):
+        return self._ws[(B, H, W)]["tok"]["iters"].cpu()

@@ -1,0 +1,175 @@
+/*
+ * disco_b200.h -- C ABI of libdisco_b200.so: the B200 (sm_100a) kernels behind the DISCO
+ * colorization forward (`AnchorColorProb.forward`, reference models/model.py:103-199).
+ *
+ * The reference is pure Python/PyTorch and has NO FFI of its own, so each
+ * entry point cites the reference *function* it replaces; the Python side that binds these symbols
+ * with ctypes is disentangledcolorization_b200/_lib.py (shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *     (the host side allocates through the torch caching allocator and passes data_ptr()).
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*).
+ *   - every call returns 0 on success or a negative disco_status; disco_last_error() returns a
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - one handle per (process, device); calls on one handle are not re-entrant (mirrors the
+ *     reference's one single-threaded Python process per GPU, train_colorizer_ddp.py:22-31).
+ *   - activations are NHWC, DISCO_F32 (exact path) or DISCO_BF16 (tensor-core path); the API-edge
+ *     tensors (gray, affinity, logits, pred_colors ...) are NCHW fp32 exactly as the reference returns.
+ */
+#ifndef DISCO_B200_H_
+#define DISCO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct disco_handle disco_handle;
+
+enum disco_status {
+  DISCO_OK = 0,
+  DISCO_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  DISCO_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed */
+  DISCO_ERR_UNSUPPORTED = -3
+};
+
+enum disco_dtype { DISCO_F32 = 0, DISCO_BF16 = 1 };
+enum disco_act { DISCO_ACT_NONE = 0, DISCO_ACT_RELU = 1, DISCO_ACT_LRELU = 2 };
+enum disco_head { DISCO_HEAD_NONE = 0, DISCO_HEAD_SOFTMAX9 = 1, DISCO_HEAD_TANH2 = 2 };
+enum disco_conv_kind { DISCO_CONV3 = 0, DISCO_DECONV4 = 1 };
+
+int disco_version(void);
+const char* disco_last_error(void);
+int disco_create(disco_handle** out, int device);
+int disco_destroy(disco_handle* h);
+/* number of kernel launches issued through this handle since creation / last reset */
+int64_t disco_launch_count(disco_handle* h);
+void disco_reset_launch_count(disco_handle* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused convolution.  Replaces every nn.Conv2d / nn.ConvTranspose2d (+ bias, activation,
+ * eval-mode BatchNorm, residual add, nn.Upsample, torch.cat, Softmax(1), tanh) call of
+ * SpixelNet / ColorProbNet / HourGlass2 (reference models/network.py:10-47,66-101,125-313 and
+ * models/model.py:196-197).
+ *
+ *   out[n,oy,ox,co] = post( act( bias[co] + res[n,oy,ox,co]
+ *                     + sum_s sum_tap sum_ci W_s[tap][ci][co] * src_s[n, iy, ix, ci] ) )
+ *   DISCO_CONV3  : iy = (oy*stride + ky - 1) >> up2_s   (zero outside the virtual (H<<up2) map)
+ *   DISCO_DECONV4: iy = (oy + 1 - ky) / 2 for ky in 0..3 where (oy + 1 - ky) is even and in range
+ *   post(v) = v*post_scale[co] + post_shift[co] (when non-NULL);  head: softmax over the 9
+ *   channels or tanh of the 2 channels, written as fp32 NCHW.
+ *
+ * Weight packing (done by the host, see engine.py):
+ *   dtype F32 : per source a block [taps][cin_s][cout] fp32, source s starting at src[s].w_off
+ *   dtype BF16: tensor-core packing described in csrc/conv_tc.cu
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;   /* NHWC activations of this source (dtype of the descriptor; `gray_f32`=1 -> fp32) */
+  int32_t H, W, C;   /* stored per-image dims */
+  int32_t up2;       /* 1: source is nearest-upsampled x2 on the fly */
+  int32_t is_f32;    /* 1: this source is fp32 even when the descriptor dtype is bf16 (the L channel) */
+  int64_t w_off;     /* element offset of this source's weight block inside `weights` */
+} disco_conv_src;
+
+typedef struct {
+  int32_t kind;      /* disco_conv_kind */
+  int32_t stride;    /* 1 | 2 (DISCO_CONV3 only) */
+  int32_t dtype;     /* disco_dtype of activations in/out */
+  int32_t batch, Ho, Wo, Cout;
+  int32_t n_src;
+  disco_conv_src src[2];
+  const void* weights;
+  const float* bias;        /* [Cout] */
+  const float* post_scale;  /* [Cout] or NULL */
+  const float* post_shift;  /* [Cout] or NULL */
+  const void* residual;     /* NHWC [batch,Ho,Wo,Cout] or NULL */
+  int32_t act;              /* disco_act */
+  float slope;              /* LeakyReLU negative slope */
+  int32_t head;             /* disco_head */
+  void* out;                /* NHWC (dtype) or, with a head, fp32 NCHW */
+} disco_conv_desc;
+
+int disco_conv(disco_handle* h, const disco_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Super-pixel pooling.  Replaces basic.poolfeat (models/basic.py:274-324) applied to
+ * cat[pred_feats, input_colors] and basic.get_spixel_size (models/basic.py:327-335), i.e.
+ * models/model.py:114-117,121, in one pass over the feature map.
+ *   feats   : NHWC [B,H,W,C] (dtype), C == 64
+ *   ab      : NCHW fp32 [B,2,H,W]
+ *   affinity: NCHW fp32 [B,9,H,W]
+ *   partial : workspace fp32 [B, H/16, W/16, 9, 68]
+ *   tokens  : fp32 [B, S, 64] (S = H/16*W/16, row-major cells)   == feat_tokens
+ *   spix_ab : fp32 NCHW [B,2,h,w]                                 == spix_colors (pooled)
+ *   conf    : fp32 [B,S]  soft mass;  sizes: fp32 [B,S]  hard-assignment mass (spixel_sizes)
+ * ------------------------------------------------------------------------------------------- */
+int disco_poolfeat(disco_handle* h, int dtype, const void* feats, const float* ab, const float* affinity,
+                   int batch, int H, int W, int C, float* partial, float* tokens, float* spix_ab,
+                   float* conf, float* sizes, void* stream);
+
+/* Replaces basic.upfeat (models/basic.py:338-376), models/model.py:195.
+ *   tokens fp32 [B,S,C] -> out NHWC [B,H,W,C] (dtype), C == 64 */
+int disco_upfeat(disco_handle* h, int dtype, const float* tokens, const float* affinity, int batch, int H, int W,
+                 int C, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Token-path linear layer: Y = epi(X' W^T + b).  Replaces the nn.Linear / in_proj / out_proj /
+ * LayerNorm calls of EncoderLayer (models/transformer2d.py:52-60), mid_word_prj / trg_word_prj
+ * (models/model.py:134-135,187-189) and the trg_word_emb hint embedding (models/model.py:175-185).
+ *   X [M,K] fp32 row-major; W [N,K]; b [N] or NULL.
+ *   pos/pos_cols/S : X' = X + pos[row % S] for output columns < pos_cols (q,k of MHA), else X' = X
+ *   col_scale/scale_cols : columns < scale_cols multiplied by col_scale after bias (q scaling)
+ *   relu; residual R [M,N] added; ln_gamma/ln_beta: LayerNorm over N (requires N == 64), eps 1e-5
+ *   hint_mask [M], labels [M], emb [314,N]: Y += hint_mask[row] * (emb[labels[row]] + emb[313])
+ *   transpose_S > 0: output written as [M/S][N][S] (the reference's permute(1,2,0).view(N,C,h,w))
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* X; const float* W; const float* b;
+  int32_t M, N, K;
+  const float* pos; int32_t pos_cols; int32_t S;
+  float col_scale; int32_t scale_cols;
+  int32_t relu;
+  const float* residual;
+  const float* ln_gamma; const float* ln_beta;
+  const float* hint_mask; const int32_t* labels; const float* emb;
+  int32_t transpose_S;
+  float* Y;
+} disco_linear_desc;
+int disco_linear(disco_handle* h, const disco_linear_desc* d, void* stream);
+
+/* Multi-head self-attention core: softmax(q k^T) v per (image, head); q already scaled.
+ * Replaces the attention inside nn.MultiheadAttention (models/transformer2d.py:36,54).
+ *   qkv [B*S, 192] (q | k | v, head h = columns 8h..8h+7 of each third) -> out [B*S, 64] */
+int disco_attention(disco_handle* h, const float* qkv, int batch, int S, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Anchor selection.  Replaces clusterkit.batch_kmeans_pytorch (models/clusterkit.py:31-58,
+ * 99-208,253-269) + AnchorAnalysis.__call__ 'clustering' (models/anchor_gen.py:92-101).
+ *   X        fp32 [B,S,64] tokens (enc_out)
+ *   init_idx int32 [B,K]   host-drawn np.random.choice(S,K,replace=False), batch order
+ *   draws    int32 [n_draws] host-pre-drawn torch.randint(S,(1,)) stream for empty clusters
+ *   sizes    fp32 [B,S]    spixel_sizes
+ *   assign   int32 [B,S]   final cluster ids (out);  hint_mask fp32 [B,S] (out)
+ *   events   int32 [B+2]   (out) per-image number of draws consumed; [B] = total; [B+1] = error flag
+ *   iters    int32 [B]     (out) Lloyd iterations executed
+ * Draw order is the reference's (image-major, then iteration, then cluster): a speculative
+ * parallel pass is followed by a sequential fix-up of the (rare) images whose draw offset moved.
+ * ------------------------------------------------------------------------------------------- */
+int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_t* init_idx, const int32_t* draws,
+                        int n_draws, const float* sizes, int batch, int S, int K, int iter_limit, float tol,
+                        int32_t* assign, float* hint_mask, int32_t* events, int32_t* iters, void* stream);
+
+/* Token labels.  mode 0: argmax over the 313 logits (== _sample_anchor_colors T=0 followed by
+ * encode_ab2ind(...).max, models/anchor_gen.py:54-66 + models/model.py:161,166);
+ * mode 1: nearest gamut bin of ab (== encode_ab2ind(ab).max, models/basic.py:177-194).
+ *   logits fp32 [B,313,S] (the pal_logit layout) or ab fp32 NCHW [B,2,h,w];  labels int32 [B*S];
+ *   colors fp32 NCHW [B,2,h,w] = q_to_ab[label]/110 (mode 0 only; NULL ok) */
+int disco_token_labels(disco_handle* h, int mode, const float* src, const float* q_to_ab, int batch, int S,
+                       int32_t* labels, float* colors, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCO_B200_H_ */
