@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- DISCO colorization forward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one `AnchorColorProb.forward(gray, ab, test_mode=True, sampled_T=0)` over one batch of
+synthetic 256x256 L-channel images (batch 64 per GPU, n_clusters=8, bf16 storage / fp32 accumulate),
+followed -- when N > 1 -- by the single NCCL all-gather of pred_colors.  Prints ONE JSON line.
+
+  value : images/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e   : images/s through the public API with pinned-host inputs copied H2D and pred_colors copied D2H
+          inside the timed region, every step
+  roofline : all conv launches of the timed workload (the tcgen05 implicit-GEMM kernel family):
+          algorithmic FLOPs / CUDA-event time per launch, summed; peak = MEASURED_PEAKS.json
+  cpu_baseline : the oracle port of the reference forward on the host cores, bounded sample
+  --impl reference : the same oracle port timed as the reference arm (the reference is pure Python on
+          torch; /root/reference does not travel to the GPU box)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 64
+H = W = 256
+K_CLUSTERS = 8
+FLOP_PER_IMAGE = 255.47e9        # SURVEY.md section 8d / BASELINE.md section 3
+METRIC = "256x256 images/sec"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples)}
+
+
+def cpu_oracle_throughput(n_images, repeats=1):
+    """images/s of the oracle port (fp32 torch CPU, all host threads) on n_images 256x256 images."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import disco_oracle as O
+    from disentangledcolorization_b200 import synth
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)
+    sd = synth.make_state_dict(seed=0)
+    gray = torch.from_numpy(synth.make_gray(n_images, H, W, seed=7))
+    ab = torch.zeros(n_images, 2, H, W)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            np.random.seed(130)
+            torch.manual_seed(130)
+            t0 = time.perf_counter()
+            O.forward(sd, gray, ab, K_CLUSTERS, 0)
+            times.append(time.perf_counter() - t0)
+    return n_images / min(times), cores, sum(times)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port), host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 2
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import disco_oracle as O
+    from disentangledcolorization_b200 import synth
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)
+    sd = synth.make_state_dict(seed=0)
+    gray = torch.from_numpy(synth.make_gray(sample, H, W, seed=7))
+    ab = torch.zeros(sample, 2, H, W)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(sd, gray, ab, K_CLUSTERS, 0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, gray, ab, K_CLUSTERS, 0)
+        dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    desc = f"{sample} of the {BATCH_PER_GPU} images of a step per timed step (oracle port of the reference forward, fp32, torch CPU)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch={BATCH_PER_GPU} 256x256 forward, n_clusters=8 (bounded sample: {sample} images/step)"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from disentangledcolorization_b200 import model, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = BATCH_PER_GPU
+    sd = synth.make_state_dict(seed=0)
+    m = model.AnchorColorProb(n_clusters=K_CLUSTERS, enhanced=True, precision=args.precision)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    eng = m.engine(dev)
+    # rank r owns images [64r, 64r+64) of the global synthetic batch
+    gray_host = torch.from_numpy(synth.make_gray(B, H, W, seed=100 + rank)).pin_memory()
+    ab_host = torch.zeros(B, 2, H, W).pin_memory()
+    gray, ab = gray_host.cuda(), ab_host.cuda()
+    gathered = torch.empty(world * B, 2, H, W, device=dev) if world > 1 else None
+    out_host = torch.empty(B, 2, H, W).pin_memory()
+
+    def step(g, a):
+        np.random.seed(130)
+        out = m(g, a, True, 0)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out[2])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(gray, ab)
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.handle.reset_launches()
+    ms = timed(lambda: step(gray, ab), args.steps)
+    launches = eng.handle.launches()
+    clocks = sampler.stop()
+
+    def e2e_step():
+        g = gray_host.cuda(non_blocking=True)
+        a = ab_host.cuda(non_blocking=True)
+        out = step(g, a)
+        out_host.copy_(out[2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    line = None
+    if rank == 0:
+        peaks, which = _peaks()
+        value = world * B * args.steps / (ms / 1e3)
+        # per-launch timing of the conv kernel family (extra steps, CUDA events around every disco_conv)
+        prof = eng.profile_convs(gray, ab, steps=2)
+        conv_flops, conv_ms = prof["flops"], prof["ms"]
+        achieved = conv_flops / (conv_ms / 1e3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        cpu_v, cores, cpu_s = cpu_oracle_throughput(8)
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"batch={B}/GPU 256x256 {args.precision} forward, n_clusters=8, 1xB200 per rank"
+                                   + (", one NCCL all-gather of pred_colors" if world > 1 else ""),
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "no explicit flush: each step streams ~10 GB of activations, far larger than the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": gray_host.numel() * 4 + ab_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "disco_conv (all conv launches of one step)",
+                         "peak_source": f"{which} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
+                         "conv_share_of_step": conv_ms / (ms / args.steps),
+                         "whole_step_frac": (B * FLOP_PER_IMAGE / (ms / args.steps / 1e3) / 1e12) / peak,
+                         "top": prof["top"]},
+            "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"8 images 256x256, oracle port of the reference forward, fp32 torch CPU, {cpu_s:.1f} s"},
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,8 @@ CONV3, DECONV4 = 0, 1
 
 EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
            "disco_reset_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
-           "disco_attention", "disco_kmeans_anchor", "disco_token_labels"]
+           "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
+           "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights"]
 
 
 class ConvSrc(C.Structure):
@@ -29,7 +30,7 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("n_src", C.c_int32),
                 ("src", ConvSrc * 2), ("weights", C.c_void_p), ("bias", C.c_void_p), ("post_scale", C.c_void_p),
                 ("post_shift", C.c_void_p), ("residual", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float),
-                ("head", C.c_int32), ("out", C.c_void_p)]
+                ("head", C.c_int32), ("out", C.c_void_p), ("gray_weights", C.c_void_p)]
 
 
 class LinearDesc(C.Structure):
@@ -66,6 +67,11 @@ def load():
     lib.disco_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     lib.disco_destroy.argtypes = [C.c_void_p]
     lib.disco_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]
+    lib.disco_set_tensor_core.argtypes = [C.c_void_p, C.c_int]
+    lib.disco_conv_tc_supported.argtypes = [C.c_void_p, C.POINTER(ConvDesc)]
+    lib.disco_conv_tc_weight_elems.argtypes = [C.POINTER(ConvDesc)]
+    lib.disco_conv_tc_weight_elems.restype = C.c_int64
+    lib.disco_conv_tc_pack_weights.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]
     lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
     lib.disco_linear.argtypes = [C.c_void_p, C.POINTER(LinearDesc), C.c_void_p]

@@ -34,6 +34,7 @@ extern "C" int disco_create(disco_handle** out, int device) {
   h->sm_count = prop.multiProcessorCount;
   h->launches = 0;
   h->tmap_encode = nullptr;
+  h->use_tc = true;
   *out = h;
   return DISCO_OK;
 }
@@ -69,6 +70,6 @@ extern "C" int disco_conv(disco_handle* h, const disco_conv_desc* d, void* strea
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->dtype == DISCO_BF16 && conv_tc_supported(d)) return conv_tc_launch(h, d, st);
+  if (d->dtype == DISCO_BF16 && h->use_tc && conv_tc_supported(d)) return conv_tc_launch(h, d, st);
   return conv_simt_launch(h, d, st);
 }

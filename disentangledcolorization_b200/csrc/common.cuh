@@ -12,6 +12,7 @@ struct disco_handle {
   int sm_count;
   int64_t launches;
   void* tmap_encode;   // cuTensorMapEncodeTiled entry point (resolved lazily)
+  bool use_tc;         // route supported bf16 descriptors to the tcgen05 kernel
 };
 
 void disco_set_error(const char* fmt, ...);

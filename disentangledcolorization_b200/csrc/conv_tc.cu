@@ -1,10 +1,682 @@
-// tcgen05 implicit-GEMM convolution (bf16 activations/weights, fp32 TMEM accumulators).
-// Placeholder until the tensor-core kernel lands: nothing is claimed supported, so disco_conv
-// routes every descriptor to the CUDA-core kernel.
+// tcgen05 implicit-GEMM convolution for sm_100a: bf16 NHWC activations, bf16 weights, fp32 accumulation in
+// tensor memory, fused epilogue (bias, residual, ReLU/LeakyReLU, post-activation BN affine, softmax9 / tanh2
+// heads, fp32 L-channel side input).
+//
+// GEMM view.  M = output pixels (a CTA tile is a TH x TW patch of NB images = 128 rows = the 128 TMEM lanes),
+// N = output channels (BN <= 256 columns per tile), K = (filter tap, input-channel chunk of KC).
+// The A operand is never materialised (no im2col): for K-block (tap, chunk) the producer issues ONE tiled TMA
+// load of the box {KC channels, TW, TH, NB} from the NHWC tensor at the tap's (dy, dx) offset.  Hardware
+// out-of-bounds zero fill implements the zero padding, and the box lands in shared memory exactly in the
+// K-major, 8-row-group, hardware-swizzled layout the UMMA shared-memory descriptor expects (row = pixel,
+// row pitch = KC*2 bytes = swizzle span).  Weights are pre-packed [K-block][Cout][KC] so a B tile is one 2-D box.
+//
+// Variants handled by the tap table built on the host (build_plan):
+//   stride 1           taps (dy,dx) in {-1,0,1}^2 on the 4-D map (C, W, H, N)
+//   stride 2           the source is viewed as a 5-D tensor (2C [x-parity, c], W/2, 2 [y-parity], H/2, N), so
+//                      "every second pixel" is a plain box with unit traversal strides
+//   nn.Upsample(x2)+conv and ConvTranspose2d(4,2,1): decomposed into 4 output-parity phases, each a 2x2-tap
+//                      convolution on the LOW-resolution source (weights pre-summed per parity); 2.25x fewer MACs
+//                      than convolving the up-sampled tensor and no up-sampled tensor in HBM
+//   two sources        (skip concat, conv8up + conv3short8): extra taps accumulate into the same TMEM tile
+//   fp32 1-channel source (the L channel beside full_feats in enhanceNet.inConv): added in the epilogue
+//
+// Warp roles (192 threads, persistent CTAs, static round-robin tile schedule):
+//   warp 0   TMA producer (one elected lane), `stages`-deep full/empty mbarrier ring
+//   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction;
+//            tcgen05.commit releases smem slots and publishes finished accumulators
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 16 columns per instruction), fused math, 32-byte vector stores.
+//            Two TMEM accumulator stages (2*BN columns) overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
-bool conv_tc_supported(const disco_conv_desc*) { return false; }
-int conv_tc_launch(disco_handle*, const disco_conv_desc*, cudaStream_t) {
-  disco_set_error("conv_tc: not built");
-  return DISCO_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int kMaxTaps = 24;
+constexpr int kThreads = 192;
+constexpr long long kSpinCycles = 6000000000ll;   // mbarrier wait watchdog (~3 s) -> trap instead of hanging the GPU
+
+struct Tap {
+  int8_t src;      // source index
+  int8_t mode;     // 0: 4-D map (c, x, y, n); 1: 5-D stride-2 map (pc, X, py, Y, n)
+  int8_t oy, ox;   // offset added to the tile origin in the source's (Y, X) index space
+  int8_t py, px;   // parities (mode 1)
+  int16_t nchunks; // input-channel chunks of KC
+  int32_t wkb0;    // first K-block row-group in the packed weight matrix
+  int32_t c_base;  // channel offset of chunk 0 inside the inner dimension (mode 1: px*C)
+};
+
+struct TcParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  Tap taps[4][kMaxTaps];
+  int32_t ntaps[4];
+  int32_t kblocks[4];         // K-blocks per phase
+  int32_t n_phase, os;        // phases (1 | 4), output stride of a phase grid (1 | 2)
+  int32_t B, Hg, Wg;          // phase-grid extent
+  int32_t TW, TH, NB;         // tile: TW*TH*NB == 128 (powers of two)
+  int32_t tw_log2, th_log2;
+  int32_t tiles_x, tiles_y, tiles_b, tiles_n, tiles_total;
+  int32_t cout_pad;           // rows per K-block in the packed weight matrix
+  // epilogue
+  int32_t Ho, Wo, Cout, act, head;
+  float slope;
+  const float* bias;
+  const float* post_scale;
+  const float* post_shift;
+  const __nv_bfloat16* residual;
+  void* out;
+  // optional fp32 single-channel 3x3 side input
+  const float* gray;
+  const float* gray_w;        // [9][Cout]
+  int32_t* error_flag;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int32_t* error_flag) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023) == 1023) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kSpinCycles) {
+        if (error_flag) atomicExch(error_flag, 1);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, rows of `KC*2` bytes = one swizzle span, 8-row groups contiguous.
+template <int KC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t layout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t sbo = (8 * KC * 2) >> 4;                      // byte distance between 8-row groups
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t instr_desc() {
+  // c_format f32 [4,6)=1, a/b format bf16 [7,10)/[10,13)=1, K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int BN, int KC>
+struct Cfg {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BYTES = BN * KC * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& phase, int& bt, int& yt, int& xt, int& nt) {
+  nt = tile % P.tiles_n; tile /= P.tiles_n;
+  xt = tile % P.tiles_x; tile /= P.tiles_x;
+  yt = tile % P.tiles_y; tile /= P.tiles_y;
+  bt = tile % P.tiles_b; tile /= P.tiles_b;
+  phase = tile;
+}
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+  using C = Cfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
+        int phase, bt, yt, xt, nt;
+        decode_tile(P, tile, phase, bt, yt, xt, nt);
+        const int x0 = xt * P.TW, y0 = yt * P.TH, b0 = bt * P.NB;
+        const int ntap = P.ntaps[phase];
+        for (int t = 0; t < ntap; ++t) {
+          const Tap tp = P.taps[phase][t];
+          for (int ch = 0; ch < tp.nchunks; ++ch) {
+            mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            void* da = smem_a + stage * C::A_BYTES;
+            void* db = smem_b + stage * C::B_BYTES;
+            if (tp.mode == 0)
+              tma_load_4d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, y0 + tp.oy, b0);
+            else
+              tma_load_5d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, tp.py, y0 + tp.oy, b0);
+            tma_load_2d(db, &P.tmB, &full[stage], 0, (tp.wkb0 + ch) * P.cout_pad + nt * BN);
+            if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc<BN>();
+      uint32_t stage = 0, ph = 0, as = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
+        const int phase = tile / (P.tiles_n * P.tiles_x * P.tiles_y * P.tiles_b);
+        const int nkb = P.kblocks[phase];
+        mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], ph, P.error_flag);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            umma_bf16(d_tmem, make_smem_desc<KC>(sa + k * 32), make_smem_desc<KC>(sb + k * 32), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;            // accumulator row = pixel within the tile
+    const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
+    uint32_t as = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
+      int phase, bt, yt, xt, nt;
+      decode_tile(P, tile, phase, bt, yt, xt, nt);
+      const int X = xt * P.TW + tx, Y = yt * P.TH + ty, b = bt * P.NB + nb;
+      const bool valid = X < P.Wg && Y < P.Hg && b < P.B;
+      const int oy = Y * P.os + (phase >> 1), ox = X * P.os + (phase & 1);
+      const size_t pix = ((size_t)b * P.Ho + oy) * P.Wo + ox;
+      const int n0 = nt * BN;
+      float g[9];
+      if (P.gray) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
+          g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
+        }
+      }
+      mbar_wait(&tfull[as], aph, P.error_flag);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      if (P.head == DISCO_HEAD_NONE) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          const int n = n0 + c0;
+          if (valid && n < P.Cout) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(P.bias + n + j);
+            if (P.gray) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(g[t], __ldg(P.gray_w + t * P.Cout + n + j), v[j]);
+            }
+            if (P.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                v[2 * j] += __low2float(h2);
+                v[2 * j + 1] += __high2float(h2);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], P.act, P.slope);
+            if (P.post_scale) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], __ldg(P.post_scale + n + j), __ldg(P.post_shift + n + j));
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n);
+            op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      } else {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        if (valid) {
+          float* outp = reinterpret_cast<float*>(P.out);
+          const size_t plane = (size_t)P.Ho * P.Wo;
+          const size_t base = (size_t)b * P.Cout * plane + (size_t)oy * P.Wo + ox;
+          if (P.head == DISCO_HEAD_SOFTMAX9) {
+            float v[9], mx = -3.4e38f, s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + __ldg(P.bias + j); mx = fmaxf(mx, v[j]); }
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
+            const float inv = 1.0f / s;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) outp[base + j * plane] = v[j] * inv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + __ldg(P.bias + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host plan
+struct Plan {
+  bool ok = false;
+  int BN = 0, KC = 0;
+  int n_phase = 1, os = 1;
+  int gray_src = -1;                 // index of the fp32 1-channel side source, or -1
+  int nkb_total = 0;                 // K-block row-groups in the packed weight matrix
+  int cout_pad = 0;
+  struct WTap { int src; int phase; int nchunks; int wkb0; std::vector<int> ktaps; };   // ktaps: reference taps summed
+  std::vector<WTap> wtaps;
+  Tap taps[4][kMaxTaps];
+  int ntaps[4] = {0, 0, 0, 0};
+  int kblocks[4] = {0, 0, 0, 0};
+};
+
+int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+
+Plan build_plan(const disco_conv_desc* d) {
+  Plan p;
+  if (d->dtype != DISCO_BF16) return p;
+  if (d->n_src < 1 || d->n_src > 2) return p;
+  int kc = 64;
+  bool any_up2 = false;
+  int n_mma_src = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    const disco_conv_src& src = d->src[s];
+    if (src.is_f32) {
+      if (src.C != 1 || d->kind != DISCO_CONV3 || d->stride != 1 || src.up2 || p.gray_src >= 0) return p;
+      p.gray_src = s;
+      continue;
+    }
+    const int k = pick_kc(src.C);
+    if (k == 0) return p;
+    kc = k < kc ? k : kc;
+    any_up2 |= src.up2 != 0;
+    n_mma_src++;
+  }
+  if (n_mma_src == 0) return p;
+  if (p.gray_src >= 0 && (d->head != DISCO_HEAD_NONE || any_up2)) return p;
+  if (d->head == DISCO_HEAD_NONE && d->Cout % 16 != 0) return p;
+  if (d->kind == DISCO_DECONV4 && d->n_src != 1) return p;
+  if (d->kind == DISCO_CONV3 && d->stride == 2 && any_up2) return p;
+  p.KC = kc;
+  const int cout16 = (d->Cout + 15) / 16 * 16;
+  p.BN = cout16 % 256 == 0 ? 256 : (cout16 % 128 == 0 ? 128 : (cout16 % 64 == 0 ? 64 : (cout16 % 32 == 0 ? 32 : 16)));
+  p.cout_pad = (d->Cout + p.BN - 1) / p.BN * p.BN;
+  const bool phased = any_up2 || d->kind == DISCO_DECONV4;
+  p.n_phase = phased ? 4 : 1;
+  p.os = phased ? 2 : 1;
+  int wkb = 0;
+  for (int ph = 0; ph < p.n_phase; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    int nt = 0;
+    for (int s = 0; s < d->n_src; ++s) {
+      if (s == p.gray_src) continue;
+      const disco_conv_src& src = d->src[s];
+      const int nch = src.C / kc;
+      auto add = [&](int mode, int oy, int ox, int ppy, int ppx, int cbase, std::vector<int> ktaps) {
+        if (nt >= kMaxTaps) { p.ok = false; nt = kMaxTaps + 1; return; }
+        Tap& t = p.taps[ph][nt++];
+        t.src = (int8_t)s; t.mode = (int8_t)mode; t.oy = (int8_t)oy; t.ox = (int8_t)ox; t.py = (int8_t)ppy; t.px = (int8_t)ppx;
+        t.nchunks = (int16_t)nch; t.wkb0 = wkb; t.c_base = cbase;
+        p.wtaps.push_back({s, ph, nch, wkb, std::move(ktaps)});
+        wkb += nch;
+        p.kblocks[ph] += nch;
+      };
+      if (d->kind == DISCO_DECONV4) {
+        // out (2i+py): py=0 <- ky=1 (row i), ky=3 (row i-1);  py=1 <- ky=0 (row i+1), ky=2 (row i)
+        const int kys[2][2] = {{1, 3}, {0, 2}}, offs[2][2] = {{0, -1}, {1, 0}};
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) add(0, offs[py][a], offs[px][b], 0, 0, 0, {kys[py][a] * 4 + kys[px][b]});
+      } else if (src.up2) {
+        // out (2i+py) <- up-sampled rows 2i+py+dy-1: py=0 -> {i-1: dy0}, {i: dy1,dy2}; py=1 -> {i: dy0,dy1}, {i+1: dy2}
+        const std::vector<int> grp[2][2] = {{{0}, {1, 2}}, {{0, 1}, {2}}};
+        const int offs[2][2] = {{-1, 0}, {0, 1}};
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            std::vector<int> kt;
+            for (int dy : grp[py][a]) for (int dx : grp[px][b]) kt.push_back(dy * 3 + dx);
+            add(0, offs[py][a], offs[px][b], 0, 0, 0, kt);
+          }
+      } else if (phased || d->stride == 2) {
+        // direct source sampled on every second pixel: v = 2i + o, o = (py|0) + dy - 1
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            const int o_y = (phased ? py : 0) + dy - 1, o_x = (phased ? px : 0) + dx - 1;
+            add(1, o_y >> 1, o_x >> 1, o_y & 1, o_x & 1, (o_x & 1) * src.C, {dy * 3 + dx});
+          }
+      } else {
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) add(0, dy - 1, dx - 1, 0, 0, 0, {dy * 3 + dx});
+      }
+    }
+    if (nt > kMaxTaps) return p;
+    p.ntaps[ph] = nt;
+  }
+  p.nkb_total = wkb;
+  p.ok = true;
+  return p;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode(disco_handle* h, CUtensorMap* tm, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, int kc) {
+  if (!h->tmap_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DISCO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      disco_set_error("cuTensorMapEncodeTiled not available from the driver");
+      return DISCO_ERR_CUDA;
+    }
+    h->tmap_encode = fn;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->tmap_encode)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims,
+                                                              strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    disco_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box0 %u)", (int)r, rank, box[0]);
+    return DISCO_ERR_CUDA;
+  }
+  return DISCO_OK;
+}
+
+int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+struct Cached {
+  TcParams params;
+  Plan plan;
+  int grid;
+};
+std::mutex g_mu;
+std::map<std::string, Cached> g_cache;
+int32_t* g_error_flag = nullptr;
+
+template <int BN, int KC>
+int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
+  using C = Cfg<BN, KC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN, KC><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
+  return DISCO_OK;
+}
+
+template <int KC>
+int launch_bn(int BN, const TcParams& P, int grid, cudaStream_t st) {
+  switch (BN) {
+    case 16: return launch_cfg<16, KC>(P, grid, st);
+    case 32: return launch_cfg<32, KC>(P, grid, st);
+    case 64: return launch_cfg<64, KC>(P, grid, st);
+    case 128: return launch_cfg<128, KC>(P, grid, st);
+    case 256: return launch_cfg<256, KC>(P, grid, st);
+  }
+  disco_set_error("conv_tc: unsupported BN %d", BN);
+  return DISCO_ERR_INVALID;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const disco_conv_desc* d) { return build_plan(d).ok; }
+
+extern "C" int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d) {
+  return h && d && h->use_tc && build_plan(d).ok ? 1 : 0;
+}
+
+extern "C" int disco_set_tensor_core(disco_handle* h, int enable) {
+  DISCO_CHECK_ARG(h != nullptr, "set_tensor_core: null handle");
+  h->use_tc = enable != 0;
+  return DISCO_OK;
+}
+
+extern "C" int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d) {
+  if (!d) return 0;
+  Plan p = build_plan(d);
+  return p.ok ? (int64_t)p.nkb_total * p.cout_pad * p.KC : 0;
+}
+
+// fp32 blocks [tap][cin_s][cout] per source (host, same layout as the CUDA-core path) -> bf16 [K-block][cout_pad][KC]
+extern "C" int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float* w32, uint16_t* out) {
+  DISCO_CHECK_ARG(d && w32 && out, "tc_pack: null pointer");
+  Plan p = build_plan(d);
+  DISCO_CHECK_ARG(p.ok, "tc_pack: descriptor not supported by the tensor-core kernel");
+  const size_t total = (size_t)p.nkb_total * p.cout_pad * p.KC;
+  memset(out, 0, total * sizeof(uint16_t));
+  for (const Plan::WTap& wt : p.wtaps) {
+    const disco_conv_src& src = d->src[wt.src];
+    const float* wb = w32 + src.w_off;
+    for (int ch = 0; ch < wt.nchunks; ++ch)
+      for (int co = 0; co < d->Cout; ++co)
+        for (int c = 0; c < p.KC; ++c) {
+          const int ci = ch * p.KC + c;
+          float s = 0.f;
+          for (int kt : wt.ktaps) s += wb[((size_t)kt * src.C + ci) * d->Cout + co];
+          __nv_bfloat16 hv = __float2bfloat16_rn(s);
+          uint16_t bits;
+          memcpy(&bits, &hv, 2);
+          out[((size_t)(wt.wkb0 + ch) * p.cout_pad + co) * p.KC + c] = bits;
+        }
+  }
+  return DISCO_OK;
+}
+
+int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
+  std::string key(reinterpret_cast<const char*>(d), sizeof(*d));
+  key.append(reinterpret_cast<const char*>(&h->device), sizeof(int));
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_cache.size() > 8192) g_cache.clear();
+  auto it = g_cache.find(key);
+  if (it == g_cache.end()) {
+    Cached c;
+    c.plan = build_plan(d);
+    DISCO_CHECK_ARG(c.plan.ok, "conv_tc: descriptor not supported");
+    const Plan& pl = c.plan;
+    TcParams& P = c.params;
+    memset(&P, 0, sizeof(P));
+    if (!g_error_flag) {
+      DISCO_CUDA(cudaMalloc(&g_error_flag, sizeof(int32_t)));
+      DISCO_CUDA(cudaMemset(g_error_flag, 0, sizeof(int32_t)));
+    }
+    P.error_flag = g_error_flag;
+    P.n_phase = pl.n_phase; P.os = pl.os;
+    P.B = d->batch; P.Hg = d->Ho / pl.os; P.Wg = d->Wo / pl.os;
+    int TW = (P.Wg % 16 == 0) ? 16 : (P.Wg % 8 == 0 ? 8 : (P.Wg % 4 == 0 ? 4 : 16));
+    if (TW > pow2_ceil(P.Wg)) TW = pow2_ceil(P.Wg);
+    int TH = 128 / TW;
+    if (TH > pow2_ceil(P.Hg)) TH = pow2_ceil(P.Hg);
+    int NB = 128 / (TW * TH);
+    P.TW = TW; P.TH = TH; P.NB = NB; P.tw_log2 = ilog2(TW); P.th_log2 = ilog2(TH);
+    P.tiles_x = (P.Wg + TW - 1) / TW; P.tiles_y = (P.Hg + TH - 1) / TH; P.tiles_b = (P.B + NB - 1) / NB;
+    P.tiles_n = pl.cout_pad / pl.BN;
+    P.tiles_total = P.tiles_x * P.tiles_y * P.tiles_b * P.tiles_n * pl.n_phase;
+    P.cout_pad = pl.cout_pad;
+    memcpy(P.taps, pl.taps, sizeof(P.taps));
+    memcpy(P.ntaps, pl.ntaps, sizeof(P.ntaps));
+    memcpy(P.kblocks, pl.kblocks, sizeof(P.kblocks));
+    P.Ho = d->Ho; P.Wo = d->Wo; P.Cout = d->Cout; P.act = d->act; P.head = d->head; P.slope = d->slope;
+    P.bias = d->bias; P.post_scale = d->post_scale; P.post_shift = d->post_shift;
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+    P.out = d->out;
+    if (pl.gray_src >= 0) {
+      P.gray = reinterpret_cast<const float*>(d->src[pl.gray_src].ptr);
+      P.gray_w = reinterpret_cast<const float*>(d->gray_weights);
+      DISCO_CHECK_ARG(P.gray_w != nullptr, "conv_tc: gray source needs desc.gray_weights (fp32 [9][Cout])");
+    }
+    // tensor maps: modes used per source
+    for (int s = 0; s < d->n_src; ++s) {
+      if (s == pl.gray_src) continue;
+      const disco_conv_src& src = d->src[s];
+      int mode = -1;
+      for (int ph = 0; ph < pl.n_phase; ++ph)
+        for (int t = 0; t < pl.ntaps[ph]; ++t)
+          if (pl.taps[ph][t].src == s) mode = pl.taps[ph][t].mode;
+      const cuuint64_t Cc = src.C, Wd = src.W, Hd = src.H, Bd = d->batch;
+      int rc;
+      if (mode == 0) {
+        cuuint64_t dims[4] = {Cc, Wd, Hd, Bd};
+        cuuint64_t str[3] = {Cc * 2, Wd * Cc * 2, Hd * Wd * Cc * 2};
+        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
+        rc = encode(h, &P.tmA[s], const_cast<void*>(src.ptr), 4, dims, str, box, pl.KC);
+      } else {
+        DISCO_CHECK_ARG(src.H % 2 == 0 && src.W % 2 == 0, "conv_tc: stride-2 source must have even H, W");
+        cuuint64_t dims[5] = {2 * Cc, Wd / 2, 2, Hd / 2, Bd};
+        cuuint64_t str[4] = {2 * Cc * 2, Wd * Cc * 2, 2 * Wd * Cc * 2, Hd * Wd * Cc * 2};
+        cuuint32_t box[5] = {(cuuint32_t)pl.KC, (cuuint32_t)TW, 1, (cuuint32_t)TH, (cuuint32_t)NB};
+        rc = encode(h, &P.tmA[s], const_cast<void*>(src.ptr), 5, dims, str, box, pl.KC);
+      }
+      if (rc != DISCO_OK) return rc;
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)pl.KC, (cuuint64_t)pl.nkb_total * pl.cout_pad};
+      cuuint64_t str[1] = {(cuuint64_t)pl.KC * 2};
+      cuuint32_t box[2] = {(cuuint32_t)pl.KC, (cuuint32_t)pl.BN};
+      int rc = encode(h, &P.tmB, const_cast<void*>(d->weights), 2, dims, str, box, pl.KC);
+      if (rc != DISCO_OK) return rc;
+    }
+    c.grid = P.tiles_total < h->sm_count ? P.tiles_total : h->sm_count;
+    it = g_cache.emplace(key, c).first;
+  }
+  const Cached& c = it->second;
+  int rc;
+  switch (c.plan.KC) {
+    case 64: rc = launch_bn<64>(c.plan.BN, c.params, c.grid, st); break;
+    case 32: rc = launch_bn<32>(c.plan.BN, c.params, c.grid, st); break;
+    case 16: rc = launch_bn<16>(c.plan.BN, c.params, c.grid, st); break;
+    default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
+  }
+  if (rc != DISCO_OK) return rc;
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
 }

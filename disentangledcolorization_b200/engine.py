@@ -59,7 +59,9 @@ class _PackedConv:
             off += blk.numel()
             blocks.append(blk.reshape(-1))
         self.op = op
-        self.w32 = torch.cat(blocks).contiguous().to(device)
+        self.w32_host = torch.cat(blocks).contiguous()
+        self.w32 = self.w32_host.to(device)
+        self.w16 = None        # tensor-core (bf16) packing, filled on first use
         self.w_off = offs
         self.bias = folded.bias.to(device)
         self.post_scale = folded.post_scale.to(device) if folded.post_scale is not None else None
@@ -86,7 +88,7 @@ class Engine:
         self._ws = {}
         self._pos = {}
         self._pending_rng = None
-        self.last_kmeans_iters = None
+        self._prof = None
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -193,7 +195,24 @@ class Engine:
         d.residual = bufs[op.res].data_ptr() if op.res else None
         d.act, d.slope, d.head = _ACT[op.act], op.slope, _HEAD[op.head]
         d.out = bufs[op.out].data_ptr()
+        self.route(d, pc)
         return d
+
+    def route(self, d, pc):
+        """Points a bf16 descriptor at the tensor-core weight packing when the tcgen05 kernel takes it."""
+        if d.dtype != _lib.BF16 or not self.lib.disco_conv_tc_supported(self.handle.h, C.byref(d)):
+            return False
+        if pc.w16 is None:
+            n = int(self.lib.disco_conv_tc_weight_elems(C.byref(d)))
+            w16 = torch.empty(n, dtype=torch.int16)
+            _lib.check(self.lib.disco_conv_tc_pack_weights(C.byref(d), C.c_void_p(pc.w32_host.data_ptr()),
+                                                           C.c_void_p(w16.data_ptr())), "disco_conv_tc_pack_weights")
+            pc.w16 = w16.to(self.device)
+        d.weights = pc.w16.data_ptr()
+        for i in range(d.n_src):
+            if d.src[i].is_f32:
+                d.gray_weights = pc.w32.data_ptr() + 4 * int(d.src[i].w_off)
+        return True
 
     def _run_net(self, net, ws, B, gray, stream):
         bufs = ws["bufs"]
@@ -204,8 +223,15 @@ class Engine:
             descs = [self._conv_desc(ws, pc, Ho, Wo, B, bufs) for pc, Ho, Wo in ws["plans"][net]]
             ws["descs"] = {k: v for k, v in ws["descs"].items() if k[0] != net}
             ws["descs"][key] = descs
-        for d in descs:
+        prof = self._prof
+        for d, (pc, _, _) in zip(descs, ws["plans"][net]):
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.check(self.lib.disco_conv(self.handle.h, C.byref(d), stream), "disco_conv")
+            if prof is not None:
+                e1.record()
+                prof.append((pc.op, d.batch, d.Ho, d.Wo, e0, e1))
 
     # ------------------------------------------------------------------ token path
     def _linear(self, stream, X, W, Y, b=None, pos=None, pos_cols=0, S=0, col_scale=1.0, scale_cols=0, relu=False,
@@ -332,6 +358,41 @@ class Engine:
         if sync_rng:
             self._resolve_rng()
         return pal_logit, ref_logit, pred, affinity.clone(), spix_colors, hint
+
+    @staticmethod
+    def algorithmic_flops(op, B, Ho, Wo):
+        """2 x MACs of the reference's own formulation of this op (9 taps at the output resolution for
+        nn.Upsample -> conv; 16 taps per input pixel for ConvTranspose2d)."""
+        if op.kind == "deconv4":
+            return 2.0 * B * (Ho // 2) * (Wo // 2) * op.cin * op.cout * 16
+        return 2.0 * B * Ho * Wo * op.cin * op.cout * 9
+
+    def profile_convs(self, gray, ab, steps=2):
+        """Times every disco_conv launch of `steps` forwards with CUDA events on the launching stream."""
+        self.forward(gray, ab)
+        torch.cuda.synchronize()
+        self._prof = []
+        try:
+            for _ in range(steps):
+                self.forward(gray, ab)
+            torch.cuda.synchronize()
+            recs = self._prof
+        finally:
+            self._prof = None
+        per_op = {}
+        flops = ms = 0.0
+        for op, B, Ho, Wo, e0, e1 in recs:
+            t = e0.elapsed_time(e1)
+            f = self.algorithmic_flops(op, B, Ho, Wo)
+            flops += f
+            ms += t
+            a = per_op.setdefault(op.name, [0.0, 0.0])
+            a[0] += f
+            a[1] += t
+        top = sorted(per_op.items(), key=lambda kv: -kv[1][1])[:6]
+        return {"flops": flops / steps, "ms": ms / steps,
+                "top": [{"op": k, "ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12} for k, v in top],
+                "per_op": {k: {"ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12} for k, v in per_op.items()}}
 
     def kmeans_iterations(self, B, H, W):
         return self._ws[(B, H, W)]["tok"]["iters"].cpu()

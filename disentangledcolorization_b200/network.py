@@ -72,6 +72,21 @@ class _ConvNet(nn.Module):
             self._engine, self._engine_key = packed, key
         return self._engine
 
+    @staticmethod
+    def _route(handle, d, pc, dev):
+        if d.dtype != _lib.BF16 or not handle.lib.disco_conv_tc_supported(handle.h, C.byref(d)):
+            return
+        if pc.w16 is None:
+            n = int(handle.lib.disco_conv_tc_weight_elems(C.byref(d)))
+            w16 = torch.empty(n, dtype=torch.int16)
+            _lib.check(handle.lib.disco_conv_tc_pack_weights(C.byref(d), C.c_void_p(pc.w32_host.data_ptr()),
+                                                             C.c_void_p(w16.data_ptr())), "disco_conv_tc_pack_weights")
+            pc.w16 = w16.to(dev)
+        d.weights = pc.w16.data_ptr()
+        for i in range(d.n_src):
+            if d.src[i].is_f32:
+                d.gray_weights = pc.w32.data_ptr() + 4 * int(d.src[i].w_off)
+
     def _run(self, inputs, out_name):
         """inputs: dict buffer-name -> tensor (gray: (N,1,H,W) fp32; others NHWC in the working dtype)."""
         from .engine import _DT, _ACT, _HEAD
@@ -107,6 +122,7 @@ class _ConvNet(nn.Module):
             d.post_shift = pc.post_shift.data_ptr() if pc.post_shift is not None else None
             d.residual = bufs[op.res].data_ptr() if op.res else None
             d.act, d.slope, d.head, d.out = _ACT[op.act], op.slope, _HEAD[op.head], out.data_ptr()
+            self._route(handle, d, pc, dev)
             _lib.check(handle.lib.disco_conv(handle.h, C.byref(d), stream), "disco_conv")
         return bufs[out_name]
 

@@ -89,9 +89,20 @@ typedef struct {
   float slope;              /* LeakyReLU negative slope */
   int32_t head;             /* disco_head */
   void* out;                /* NHWC (dtype) or, with a head, fp32 NCHW */
+  const float* gray_weights; /* tensor-core path only: fp32 [9][Cout] weights of the fp32 1-channel source */
 } disco_conv_desc;
 
 int disco_conv(disco_handle* h, const disco_conv_desc* d, void* stream);
+
+/* Tensor-core (tcgen05) routing of bf16 descriptors.  disco_conv sends a DISCO_BF16 descriptor to the tcgen05
+ * implicit-GEMM kernel when disco_conv_tc_supported() is 1; `weights` must then hold the bf16 packing produced by
+ * disco_conv_tc_pack_weights (host-side repack of the fp32 [tap][cin][cout] blocks; both pointers are HOST
+ * pointers there, `src[].w_off` and `src[].C` of the descriptor describe the fp32 blocks).  Otherwise the
+ * descriptor runs on the CUDA-core kernel with fp32 weights. */
+int disco_set_tensor_core(disco_handle* h, int enable);
+int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d);
+int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d);
+int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float* w_f32_host, uint16_t* w_bf16_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Super-pixel pooling.  Replaces basic.poolfeat (models/basic.py:274-324) applied to

@@ -30,7 +30,7 @@ def test_struct_layout_matches_header():
     """ctypes mirrors of the descriptor structs have the C layout (sizes from the compiler's rules)."""
     from disentangledcolorization_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSrc) == 40
-    assert ctypes.sizeof(_lib.ConvDesc) == 32 + 80 + 5 * 8 + 16 + 8
+    assert ctypes.sizeof(_lib.ConvDesc) == 32 + 80 + 5 * 8 + 16 + 8 + 8
     assert _lib.ConvDesc.src.offset == 32 and _lib.ConvDesc.out.offset == 168
     assert ctypes.sizeof(_lib.LinearDesc) == 136
 
