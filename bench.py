@@ -51,10 +51,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -63,10 +63,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
@@ -155,6 +155,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B = BATCH_PER_GPU
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     sd = synth.make_state_dict(seed=0)
     m = model.AnchorColorProb(n_clusters=K_CLUSTERS, enhanced=True, precision=args.precision)
     m.load_state_dict(sd, strict=True)
@@ -194,8 +200,11 @@ def run_ours(args):
             ms = float(t)
         return ms
 
+    log("model + inputs ready")
     for _ in range(max(args.warmup, 3)):
         step(gray, ab)
+    torch.cuda.synchronize()
+    log("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     eng.handle.reset_launches()
@@ -210,8 +219,10 @@ def run_ours(args):
         out_host.copy_(out[2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    log(f"timed region done: {ms / args.steps:.2f} ms/step")
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    log(f"e2e done: {ms_e2e / args.steps:.2f} ms/step")
 
     line = None
     if rank == 0:
@@ -222,7 +233,12 @@ def run_ours(args):
         conv_flops, conv_ms = prof["flops"], prof["ms"]
         achieved = conv_flops / (conv_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        cpu_v, cores, cpu_s = cpu_oracle_throughput(8)
+        log("conv profile done")
+        if args.dump_profile:
+            with open(args.dump_profile, "w") as f:
+                json.dump({"ms_per_step": ms / args.steps, "conv_ms": conv_ms, "per_op": prof["per_op"]}, f, indent=1)
+        cpu_v, cores, cpu_s = (0.0, os.cpu_count(), 0.0) if args.no_cpu_baseline else cpu_oracle_throughput(8)
+        log("cpu baseline done")
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -260,6 +276,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dump-profile", default=None, help="write the per-op conv timing table (JSON) to this path")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -180,11 +180,87 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams P) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cin == 1 first layers (repnet.conv1_2.0: 1->64, segnet.conv0a: 1->16): HBM-bound (4 B in, 2*Cout B out
+// per pixel).  One thread = one pixel x 8 output channels; its 72 weights stay in registers across a
+// grid-stride loop; a warp writes 32 x 16 B = 512 contiguous bytes of the NHWC output.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_c1_kernel(const float* __restrict__ gray, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, const float* __restrict__ ps,
+                                                      const float* __restrict__ pb, int B, int H, int W, int Cout, int act,
+                                                      float slope, T* __restrict__ out) {
+  const int tpp = Cout >> 3;                       // threads per pixel
+  const unsigned total = (unsigned)H * W * tpp;    // work items per image (blockIdx.y = image)
+  const int c0 = (threadIdx.x % tpp) * 8;          // blockDim.x is a multiple of tpp
+  float wr[9][8], br[8], sr[8], hr[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = w[t * Cout + c0 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = bias[c0 + j];
+    sr[j] = ps ? ps[c0 + j] : 1.f;
+    hr[j] = pb ? pb[c0 + j] : 0.f;
+  }
+  const size_t n = blockIdx.y;
+  const float* g = gray + n * H * W;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix_in = i / tpp;
+    const int x = (int)(pix_in % (unsigned)W), y = (int)(pix_in / (unsigned)W);
+    const size_t pix = n * H * W + pix_in;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = br[j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const float gv = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(g + yy * W + xx) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(gv, wr[t][j], v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, slope) * sr[j] + hr[j];
+    T* o = out + pix * Cout + c0;
+    if (sizeof(T) == 2) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else {
+      float* of = reinterpret_cast<float*>(o);
+      *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
 }  // namespace
 
 int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   DISCO_CHECK_ARG(d->n_src >= 1 && d->n_src <= 2, "conv: n_src must be 1 or 2");
   DISCO_CHECK_ARG(d->head == DISCO_HEAD_NONE || d->Cout <= TC, "conv: head needs Cout <= 64");
+  // dedicated kernel for the single-channel fp32 input layers (bf16 storage path only: the fp32 exact path keeps
+  // the reference summation structure of the generic kernel)
+  if (d->dtype == DISCO_BF16 && d->kind == DISCO_CONV3 && d->n_src == 1 && d->src[0].C == 1 && d->src[0].is_f32 &&
+      d->stride == 1 && !d->src[0].up2 && d->head == DISCO_HEAD_NONE && !d->residual && d->Cout % 8 == 0 &&
+      256 % (d->Cout / 8) == 0 && d->batch <= 65535 && (long long)d->Ho * d->Wo * (d->Cout / 8) < (1ll << 31)) {
+    const long long items = (long long)d->Ho * d->Wo * (d->Cout / 8);     // per image
+    long long bx = (items + 255) / 256;
+    const long long cap = ((long long)h->sm_count * 16 + d->batch - 1) / d->batch;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    conv_c1_kernel<__nv_bfloat16><<<dim3((unsigned)bx, d->batch), 256, 0, st>>>(
+        reinterpret_cast<const float*>(d->src[0].ptr), reinterpret_cast<const float*>(d->weights) + d->src[0].w_off, d->bias,
+        d->post_scale, d->post_shift, d->batch, d->Ho, d->Wo, d->Cout, d->act, d->slope,
+        reinterpret_cast<__nv_bfloat16*>(d->out));
+    DISCO_LAUNCH_CHECK(h);
+    return DISCO_OK;
+  }
   SimtParams P;
   P.d = *d;
   dim3 grid(((d->Wo + 7) / 8) * ((d->Ho + 7) / 8), (d->Cout + TC - 1) / TC, d->batch);

@@ -133,6 +133,15 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -154,6 +163,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
 }
 
 // K-major operand tile in shared memory, rows of `KC*2` bytes = one swizzle span, 8-row groups contiguous.
@@ -178,7 +204,10 @@ struct Cfg {
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // per-epilogue-warp parameter cache: bias | post_scale | post_shift (+ 9 x fp32 L-channel weights when BN <= 64)
+  static constexpr int EPI_FLOATS = 3 * BN + (BN <= 64 ? 9 * BN : 0);
+  static constexpr int EPI_BYTES = 4 * EPI_FLOATS * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 __device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& phase, int& bt, int& yt, int& xt, int& nt) {
@@ -202,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_params = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -223,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, ph = 0;
       for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
         int phase, bt, yt, xt, nt;
@@ -249,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = instr_desc<BN>();
       uint32_t stage = 0, ph = 0, as = 0, aph = 0;
       for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
@@ -279,6 +309,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;            // accumulator row = pixel within the tile
     const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
+    float* wp = epi_params + (warp - 2) * C::EPI_FLOATS;    // this warp's private parameter cache
+    int cached_nt = -1;
+    constexpr int CH = BN >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
     uint32_t as = 0, aph = 0;
     for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
       int phase, bt, yt, xt, nt;
@@ -288,12 +321,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int oy = Y * P.os + (phase >> 1), ox = X * P.os + (phase & 1);
       const size_t pix = ((size_t)b * P.Ho + oy) * P.Wo + ox;
       const int n0 = nt * BN;
-      float g[9];
-      if (P.gray) {
+      if (nt != cached_nt) {
+        for (int j = lane; j < BN; j += 32) {
+          const int n = n0 + j;
+          const bool ok = n < P.Cout;
+          wp[j] = ok ? P.bias[n] : 0.f;
+          wp[BN + j] = (ok && P.post_scale) ? P.post_scale[n] : 1.f;
+          wp[2 * BN + j] = (ok && P.post_shift) ? P.post_shift[n] : 0.f;
+          if constexpr (BN <= 64) {
+            if (P.gray) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
-          g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
+              for (int t = 0; t < 9; ++t) wp[(3 + t) * BN + j] = ok ? P.gray_w[t * P.Cout + n] : 0.f;
+            }
+          }
+        }
+        cached_nt = nt;
+        __syncwarp();
+      }
+      float g[9];
+      if constexpr (BN <= 64) {
+        if (P.gray) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
+            g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
+          }
         }
       }
       mbar_wait(&tfull[as], aph, P.error_flag);
@@ -301,46 +353,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       if (P.head == DISCO_HEAD_NONE) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          const int n = n0 + c0;
-          if (valid && n < P.Cout) {
-            float v[16];
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t r[CH];
+          tmem_ld<CH>(taddr + c0, r);
+          if (valid && n0 + c0 < P.Cout) {
+            float v[CH];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __ldg(P.bias + n + j);
-            if (P.gray) {
+            for (int j = 0; j < CH; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(wp + c0 + j);
+              v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+              v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+            }
+            if constexpr (BN <= 64) {
+              if (P.gray) {
 #pragma unroll
-              for (int t = 0; t < 9; ++t)
+                for (int t = 0; t < 9; ++t)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaf(g[t], __ldg(P.gray_w + t * P.Cout + n + j), v[j]);
+                  for (int j = 0; j < CH; j += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + (3 + t) * BN + c0 + j);
+                    v[j] = fmaf(g[t], wv.x, v[j]); v[j + 1] = fmaf(g[t], wv.y, v[j + 1]);
+                    v[j + 2] = fmaf(g[t], wv.z, v[j + 2]); v[j + 3] = fmaf(g[t], wv.w, v[j + 3]);
+                  }
+              }
             }
             if (P.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n);
-              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n0 + c0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                v[2 * j] += __low2float(h2);
-                v[2 * j + 1] += __high2float(h2);
+              for (int u = 0; u < CH / 8; ++u) {
+                const uint4 rr = __ldg(rp + u);
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                  v[u * 8 + 2 * j] += __low2float(h2);
+                  v[u * 8 + 2 * j + 1] += __high2float(h2);
+                }
               }
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], P.act, P.slope);
+            for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], P.act, P.slope);
             if (P.post_scale) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], __ldg(P.post_scale + n + j), __ldg(P.post_shift + n + j));
+              for (int j = 0; j < CH; j += 4) {
+                const float4 sv = *reinterpret_cast<const float4*>(wp + BN + c0 + j);
+                const float4 hv = *reinterpret_cast<const float4*>(wp + 2 * BN + c0 + j);
+                v[j] = fmaf(v[j], sv.x, hv.x); v[j + 1] = fmaf(v[j + 1], sv.y, hv.y);
+                v[j + 2] = fmaf(v[j + 2], sv.z, hv.z); v[j + 3] = fmaf(v[j + 3], sv.w, hv.w);
+              }
             }
-            uint32_t w[8];
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n0 + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int u = 0; u < CH / 8; ++u) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[u] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n);
-            op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            op[1] = make_uint4(w[4], w[5], w[6], w[7]);
           }
         }
       } else {
@@ -353,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (P.head == DISCO_HEAD_SOFTMAX9) {
             float v[9], mx = -3.4e38f, s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + __ldg(P.bias + j); mx = fmaxf(mx, v[j]); }
+            for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + wp[j]; mx = fmaxf(mx, v[j]); }
 #pragma unroll
             for (int j = 0; j < 9; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
             const float inv = 1.0f / s;
@@ -361,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < 9; ++j) outp[base + j * plane] = v[j] * inv;
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + __ldg(P.bias + j));
+            for (int j = 0; j < 2; ++j) outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + wp[j]);
           }
         }
       }
@@ -425,6 +496,7 @@ Plan build_plan(const disco_conv_desc* d) {
   p.KC = kc;
   const int cout16 = (d->Cout + 15) / 16 * 16;
   p.BN = cout16 % 256 == 0 ? 256 : (cout16 % 128 == 0 ? 128 : (cout16 % 64 == 0 ? 64 : (cout16 % 32 == 0 ? 32 : 16)));
+  if (p.gray_src >= 0 && p.BN > 64) return p;
   p.cout_pad = (d->Cout + p.BN - 1) / p.BN * p.BN;
   const bool phased = any_up2 || d->kind == DISCO_DECONV4;
   p.n_phase = phased ? 4 : 1;

@@ -174,36 +174,53 @@ struct KmArgs {
   int32_t* assign; float* hint_mask; int32_t* events; int32_t* iters;
 };
 
-// Runs one image.  Returns (through smem scalars) the number of draws consumed.
+// Runs one image.  XT: optional shared-memory copy of the image's tokens, transposed and padded:
+// XT[c * (S + 1) + t] (conflict-free for both "thread = token" and "thread = (cluster, channel)" access).
 __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float* C, float* Cprev, int* cnt,
-                                 int* ridx, float* shiftk, int* s_flag) {
+                                 int* ridx, float* shiftk, int* s_flag, float* XT, int* s_assign) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int S = a.S, K = a.K;
+  const int S = a.S, K = a.K, SP1 = S + 1;
   const float* X = a.X + (size_t)n * S * KD;
   int32_t* assign = a.assign + (size_t)n * S;
+  if (XT) {
+    for (int e = tid; e < S * KD; e += nt) XT[(e % KD) * SP1 + e / KD] = X[e];
+  }
   for (int e = tid; e < K * KD; e += nt) C[e] = X[(size_t)a.init_idx[n * K + e / KD] * KD + (e % KD)];
   if (tid == 0) { s_flag[0] = 0; /* events */ s_flag[1] = 0; /* stop */ s_flag[2] = 0; /* iterations */ }
   __syncthreads();
   while (true) {
     // 1. assignment (first minimum wins, like torch.argmin)
     for (int t = tid; t < S; t += nt) {
-      const float* x = X + (size_t)t * KD;
-      float best = FLT_MAX; int bi = 0;
-      for (int k = 0; k < K; ++k) {
-        float dsum = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < KD; ++c) { const float df = x[c] - C[k * KD + c]; dsum = fmaf(df, df, dsum); }
-        if (dsum < best) { best = dsum; bi = k; }
+      float dk[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) dk[k] = 0.f;
+      for (int c = 0; c < KD; ++c) {
+        const float xv = XT ? XT[c * SP1 + t] : X[(size_t)t * KD + c];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) { const float df = xv - C[k * KD + c]; dk[k] = fmaf(df, df, dk[k]); }
       }
+      float best = FLT_MAX; int bi = 0;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K && dk[k] < best) { best = dk[k]; bi = k; }
+      if (s_assign) s_assign[t] = bi;
       assign[t] = bi;
     }
     for (int e = tid; e < K * KD; e += nt) Cprev[e] = C[e];
     __syncthreads();
-    // 2. member counts, then draws for empty clusters in cluster order (reference: clusterkit.py:178-184)
-    for (int k = tid; k < K; k += nt) {
-      int c = 0;
-      for (int t = 0; t < S; ++t) c += (assign[t] == k);
-      cnt[k] = c;
+    // 2. member counts (one warp per cluster), then draws for empty clusters in cluster order
+    //    (reference: clusterkit.py:178-184)
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      const int* asg = s_assign ? s_assign : assign;
+      for (int k = warp; k < K; k += nw) {
+        int c = 0;
+        for (int t = lane; t < S; t += 32) c += (asg[t] == k);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[k] = c;
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -218,17 +235,25 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
     }
     __syncthreads();
     // 3. centre update: mean of members in token order
-    for (int e = tid; e < K * KD; e += nt) {
-      const int k = e / KD, c = e % KD;
-      float v;
-      if (cnt[k] == 0) {
-        v = X[(size_t)ridx[k] * KD + c];
-      } else {
-        float s = 0.f;
-        for (int t = 0; t < S; ++t) if (assign[t] == k) s += X[(size_t)t * KD + c];
-        v = s / (float)cnt[k];
+    {
+      const int* asg = s_assign ? s_assign : assign;
+      for (int e = tid; e < K * KD; e += nt) {
+        const int k = e / KD, c = e % KD;
+        float v;
+        if (cnt[k] == 0) {
+          v = X[(size_t)ridx[k] * KD + c];
+        } else {
+          float s = 0.f;
+          if (XT) {
+            const float* col = XT + c * SP1;
+            for (int t = 0; t < S; ++t) if (asg[t] == k) s += col[t];
+          } else {
+            for (int t = 0; t < S; ++t) if (asg[t] == k) s += X[(size_t)t * KD + c];
+          }
+          v = s / (float)cnt[k];
+        }
+        C[e] = v;
       }
-      C[e] = v;
     }
     __syncthreads();
     // 4. centre shift = sum_k ||c_k - c_k_prev||
@@ -251,13 +276,23 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
   float* hint = a.hint_mask + (size_t)n * S;
   for (int t = tid; t < S; t += nt) hint[t] = 0.f;
   __syncthreads();
-  for (int k = tid; k < K; k += nt) {
-    float best = -FLT_MAX; int bi = 0;
-    for (int t = 0; t < S; ++t) {
-      const float sc = (assign[t] == k ? 1.0f : 0.0f) + a.sizes[(size_t)n * S + t] * 0.01f;
-      if (sc > best) { best = sc; bi = t; }
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const int* asg = s_assign ? s_assign : assign;
+    for (int k = warp; k < K; k += nw) {
+      float best = -FLT_MAX; int bi = 0x7fffffff;
+      for (int t = lane; t < S; t += 32) {
+        const float sc = (asg[t] == k ? 1.0f : 0.0f) + a.sizes[(size_t)n * S + t] * 0.01f;
+        if (sc > best) { best = sc; bi = t; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) ridx[k] = bi;
     }
-    ridx[k] = bi;
   }
   __syncthreads();
   if (tid == 0) {
@@ -269,20 +304,24 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
 }
 
 // mode 0: grid B, speculative (draw offset 0).  mode 1: grid 1, sequential fix-up in image order.
-__global__ void __launch_bounds__(256) kmeans_anchor_kernel(const KmArgs a, int mode) {
+// Dynamic shared memory (when it fits): transposed tokens XT[64][S+1] followed by int assign[S].
+__global__ void __launch_bounds__(256) kmeans_anchor_kernel(const KmArgs a, int mode, int use_smem) {
   __shared__ float C[KMAX * KD];
   __shared__ float Cprev[KMAX * KD];
   __shared__ int cnt[KMAX];
   __shared__ int ridx[KMAX];
   __shared__ float shiftk[KMAX];
   __shared__ int s_flag[4];
+  extern __shared__ float km_dyn[];
+  float* XT = use_smem ? km_dyn : nullptr;
+  int* s_assign = use_smem ? reinterpret_cast<int*>(km_dyn + KD * (a.S + 1)) : nullptr;
   if (mode == 0) {
-    kmeans_one_image(a, blockIdx.x, 0, C, Cprev, cnt, ridx, shiftk, s_flag);
+    kmeans_one_image(a, blockIdx.x, 0, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign);
   } else {
     int running = 0;
     for (int n = 0; n < a.B; ++n) {
       const int ev = a.events[n];
-      if (ev > 0 && running > 0) kmeans_one_image(a, n, running, C, Cprev, cnt, ridx, shiftk, s_flag);
+      if (ev > 0 && running > 0) kmeans_one_image(a, n, running, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign);
       __syncthreads();
       running += a.events[n];
       __syncthreads();
@@ -355,9 +394,13 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   KmArgs a{X, init_idx, draws, n_draws, sizes, batch, S, K, iter_limit, tol, assign, hint_mask, events, iters};
   cudaStream_t st = (cudaStream_t)stream;
   DISCO_CUDA(cudaMemsetAsync(events, 0, sizeof(int32_t) * (batch + 2), st));
-  kmeans_anchor_kernel<<<batch, 256, 0, st>>>(a, 0);
+  const size_t dyn = ((size_t)KD * (S + 1) + S) * sizeof(float);
+  const int use_smem = dyn <= 160 * 1024;
+  if (use_smem && dyn > 32 * 1024)
+    DISCO_CUDA(cudaFuncSetAttribute(kmeans_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  kmeans_anchor_kernel<<<batch, 256, use_smem ? dyn : 0, st>>>(a, 0, use_smem);
   DISCO_LAUNCH_CHECK(h);
-  kmeans_anchor_kernel<<<1, 256, 0, st>>>(a, 1);
+  kmeans_anchor_kernel<<<1, 256, use_smem ? dyn : 0, st>>>(a, 1, use_smem);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }

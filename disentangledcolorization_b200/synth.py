@@ -33,8 +33,21 @@ def _unit(x):
     return x / max(np.linalg.norm(x), 1e-12)
 
 
+_CACHE = {}
+
+
 def make_state_dict(seed=0, calib=None, as_torch=True):
     """Returns an OrderedDict key -> tensor (fp32; num_batches_tracked int64) with all 461 entries."""
+    from collections import OrderedDict
+    if calib is None and as_torch and seed in _CACHE:
+        return OrderedDict((k, v.clone()) for k, v in _CACHE[seed].items())
+    res = _make_state_dict(seed, calib, as_torch)
+    if calib is None and as_torch:
+        _CACHE[seed] = OrderedDict((k, v.clone()) for k, v in res.items())
+    return res
+
+
+def _make_state_dict(seed, calib, as_torch):
     from collections import OrderedDict
     rng = np.random.Generator(np.random.PCG64(seed))
     calib = _load_calib() if calib is None else calib
