@@ -20,14 +20,15 @@
 //   two sources        (skip concat, conv8up + conv3short8): extra taps accumulate into the same TMEM tile
 //   fp32 1-channel source (the L channel beside full_feats in enhanceNet.inConv): added in the epilogue
 //
-// Warp roles (192 threads, persistent CTAs, static round-robin tile schedule):
+// Warp roles (320 threads, persistent CTAs, static round-robin tile schedule):
 //   warp 0   TMA producer (one elected lane), `stages`-deep full/empty mbarrier ring
 //   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction;
 //            tcgen05.commit releases smem slots and publishes finished accumulators
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 16 columns per instruction), fused math, 32-byte vector stores.
+//   warps 2-9 epilogue: tcgen05.ld (32 lanes x 16/32 columns per instruction), fused math, 16-byte vector stores.
 //            Two TMEM accumulator stages (2*BN columns) overlap the epilogue of tile i with the MMAs of tile i+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -37,7 +38,7 @@
 namespace {
 
 constexpr int kMaxTaps = 24;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr long long kSpinCycles = 6000000000ll;   // mbarrier wait watchdog (~3 s) -> trap instead of hanging the GPU
 
 struct Tap {
@@ -50,9 +51,24 @@ struct Tap {
   int32_t c_base;  // channel offset of chunk 0 inside the inner dimension (mode 1: px*C)
 };
 
+// One pipeline step of the resident-weight kernel: ONE TMA load of an activation sub-tile that serves up to three
+// filter taps (the taps of one filter column: same dx, dy = -1,0,+1 -> the box carries TH+2 rows and each tap's
+// A operand starts `dy*TW` rows further down, which keeps the start address on a swizzle-atom boundary).
+struct Step {
+  int8_t src, mode, ox, oy, py, px, ntap, pad;
+  int32_t c0;          // inner-dimension start coordinate (channel chunk, + px*C for the stride-2 view)
+  uint32_t bytes;      // bytes the load delivers
+  uint32_t tap[3];     // (A start offset in bytes >> 4) | (resident weight block index << 16)
+};
+constexpr int kMaxSteps = 16;
+
 struct TcParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
+  Step steps[4][kMaxSteps];
+  int32_t nsteps[4];
+  int32_t wkb_phase0[4];      // first weight K-block of each phase in the packed matrix
+  int32_t res_stages, res_a_stage_bytes, res_b_bytes;
   Tap taps[4][kMaxTaps];
   int32_t ntaps[4];
   int32_t kblocks[4];         // K-blocks per phase
@@ -133,6 +149,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -206,8 +235,34 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // per-epilogue-warp parameter cache: bias | post_scale | post_shift (+ 9 x fp32 L-channel weights when BN <= 64)
   static constexpr int EPI_FLOATS = 3 * BN + (BN <= 64 ? 9 * BN : 0);
-  static constexpr int EPI_BYTES = 4 * EPI_FLOATS * 4;
+  static constexpr int EPI_BYTES = 8 * EPI_FLOATS * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
+};
+
+// Mixed-radix tile counter (n fastest, then x, y, image, phase) advanced by gridDim.x per iteration without
+// integer division in the loop.
+struct TileIter {
+  int nt, xt, yt, bt, phase;
+  int dn, dx, dy, db, dp;
+  __device__ __forceinline__ void init(const TcParams& P, int tile, int step) {
+    int t = tile;
+    nt = t % P.tiles_n; t /= P.tiles_n;
+    xt = t % P.tiles_x; t /= P.tiles_x;
+    yt = t % P.tiles_y; t /= P.tiles_y;
+    bt = t % P.tiles_b; phase = t / P.tiles_b;
+    t = step;
+    dn = t % P.tiles_n; t /= P.tiles_n;
+    dx = t % P.tiles_x; t /= P.tiles_x;
+    dy = t % P.tiles_y; t /= P.tiles_y;
+    db = t % P.tiles_b; dp = t / P.tiles_b;
+  }
+  __device__ __forceinline__ void next(const TcParams& P) {
+    nt += dn; int c = nt >= P.tiles_n; nt -= c ? P.tiles_n : 0;
+    xt += dx + c; c = xt >= P.tiles_x; xt -= c ? P.tiles_x : 0;
+    yt += dy + c; c = yt >= P.tiles_y; yt -= c ? P.tiles_y : 0;
+    bt += db + c; c = bt >= P.tiles_b; bt -= c ? P.tiles_b : 0;
+    phase += dp + c;
+  }
 };
 
 __device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& phase, int& bt, int& yt, int& xt, int& nt) {
@@ -216,6 +271,164 @@ __device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& ph
   yt = tile % P.tiles_y; tile /= P.tiles_y;
   bt = tile % P.tiles_b; tile /= P.tiles_b;
   phase = tile;
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue
+// Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
+// lane quarter (w & 3) (a hardware restriction) and, when BN >= 32, the column half ((w - 2) >> 2): two warps per
+// SM sub-partition keep the epilogue's issue rate up (one warp alone runs at IPC ~0.2 on dependent fp32 math).
+template <int BN>
+__device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                              float* epi_params, int warp, int lane) {
+  constexpr int EPI_FLOATS = 3 * BN + (BN <= 64 ? 9 * BN : 0);
+  constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
+  constexpr int NHALF = BN >= 32 ? 2 : 1;       // column halves (one per warp of a lane quarter)
+  constexpr int COLS = BN / NHALF;              // columns this warp owns
+  const int q = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const bool active = half < NHALF;
+  const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
+  const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
+  const uint32_t wp = smem_u32(epi_params + (warp - 2) * EPI_FLOATS);   // this warp's private parameter cache
+  const int col0 = half * COLS;
+  int cached_nt = -1;
+  uint32_t as = 0, aph = 0;
+  TileIter it;
+  it.init(P, blockIdx.x, gridDim.x);
+  for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+    const int phase = it.phase, nt = it.nt;
+    const int X = it.xt * P.TW + tx, Y = it.yt * P.TH + ty, b = it.bt * P.NB + nb;
+    const bool valid = active && X < P.Wg && Y < P.Hg && b < P.B;
+    const int oy = Y * P.os + (phase >> 1), ox = X * P.os + (phase & 1);
+    const size_t pix = ((size_t)b * P.Ho + oy) * P.Wo + ox;
+    const int n0 = nt * BN;
+    if (nt != cached_nt) {
+      for (int j = lane; j < BN; j += 32) {
+        const int n = n0 + j;
+        const bool ok = n < P.Cout;
+        sts32(wp + 4 * j, ok ? P.bias[n] : 0.f);
+        sts32(wp + 4 * (BN + j), (ok && P.post_scale) ? P.post_scale[n] : 1.f);
+        sts32(wp + 4 * (2 * BN + j), (ok && P.post_shift) ? P.post_shift[n] : 0.f);
+        if constexpr (BN <= 64) {
+          if (P.gray) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) sts32(wp + 4 * ((3 + t) * BN + j), ok ? P.gray_w[t * P.Cout + n] : 0.f);
+          }
+        }
+      }
+      cached_nt = nt;
+      __syncwarp();
+    }
+    float g[9];
+    if constexpr (BN <= 64) {
+      if (P.gray) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
+          g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
+        }
+      }
+    }
+    mbar_wait(&tfull[as], aph, P.error_flag);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+    if (P.head == DISCO_HEAD_NONE) {
+      if (active) {
+#pragma unroll 1
+        for (int c0 = col0; c0 < col0 + COLS; c0 += CH) {
+          uint32_t r[CH];
+          tmem_ld<CH>(taddr + c0, r);
+          if (valid && n0 + c0 < P.Cout) {
+            float v[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 bv = lds128(wp + 4 * (c0 + j));
+              v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+              v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+            }
+            if constexpr (BN <= 64) {
+              if (P.gray) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                  for (int j = 0; j < CH; j += 4) {
+                    const float4 wv = lds128(wp + 4 * ((3 + t) * BN + c0 + j));
+                    v[j] = fmaf(g[t], wv.x, v[j]); v[j + 1] = fmaf(g[t], wv.y, v[j + 1]);
+                    v[j + 2] = fmaf(g[t], wv.z, v[j + 2]); v[j + 3] = fmaf(g[t], wv.w, v[j + 3]);
+                  }
+              }
+            }
+            if (P.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n0 + c0);
+#pragma unroll
+              for (int u = 0; u < CH / 8; ++u) {
+                const uint4 rr = __ldg(rp + u);
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                  v[u * 8 + 2 * j] += __low2float(h2);
+                  v[u * 8 + 2 * j + 1] += __high2float(h2);
+                }
+              }
+            }
+            if (P.act == DISCO_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (P.act == DISCO_ACT_LRELU) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], v[j] * P.slope);   // slope in [0,1)
+            }
+            if (P.post_scale) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 sv = lds128(wp + 4 * (BN + c0 + j));
+                const float4 hv = lds128(wp + 4 * (2 * BN + c0 + j));
+                v[j] = fmaf(v[j], sv.x, hv.x); v[j + 1] = fmaf(v[j + 1], sv.y, hv.y);
+                v[j + 2] = fmaf(v[j + 2], sv.z, hv.z); v[j + 3] = fmaf(v[j + 3], sv.w, hv.w);
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n0 + c0);
+#pragma unroll
+            for (int u = 0; u < CH / 8; ++u) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[u] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+    } else if (active) {
+      uint32_t r[16];
+      tmem_ld16(taddr, r);
+      if (valid) {
+        float* outp = reinterpret_cast<float*>(P.out);
+        const size_t plane = (size_t)P.Ho * P.Wo;
+        const size_t base = (size_t)b * P.Cout * plane + (size_t)oy * P.Wo + ox;
+        if (P.head == DISCO_HEAD_SOFTMAX9) {
+          float v[9], mx = -3.4e38f, s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + lds32(wp + 4 * j); mx = fmaxf(mx, v[j]); }
+#pragma unroll
+          for (int j = 0; j < 9; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
+          const float inv = 1.0f / s;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) outp[base + j * plane] = v[j] * inv;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + lds32(wp + 4 * j));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[as]);
+    if (++as == 2) { as = 0; aph ^= 1; }
+  }
 }
 
 template <int BN, int KC>
@@ -237,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -255,10 +468,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===================================================================== TMA producer
     if (elect_one()) {
       uint32_t stage = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
-        int phase, bt, yt, xt, nt;
-        decode_tile(P, tile, phase, bt, yt, xt, nt);
-        const int x0 = xt * P.TW, y0 = yt * P.TH, b0 = bt * P.NB;
+      TileIter it;
+      it.init(P, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+        const int phase = it.phase, nt = it.nt;
+        const int x0 = it.xt * P.TW, y0 = it.yt * P.TH, b0 = it.bt * P.NB;
         const int ntap = P.ntaps[phase];
         for (int t = 0; t < ntap; ++t) {
           const Tap tp = P.taps[phase][t];
@@ -282,8 +496,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc<BN>();
       uint32_t stage = 0, ph = 0, as = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
-        const int phase = tile / (P.tiles_n * P.tiles_x * P.tiles_y * P.tiles_b);
+      TileIter it;
+      it.init(P, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+        const int phase = it.phase;
         const int nkb = P.kblocks[phase];
         mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
         tc_fence_after();
@@ -305,142 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;            // accumulator row = pixel within the tile
-    const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
-    float* wp = epi_params + (warp - 2) * C::EPI_FLOATS;    // this warp's private parameter cache
-    int cached_nt = -1;
-    constexpr int CH = BN >= 32 ? 32 : 16;  // accumulator columns per tcgen05.ld
-    uint32_t as = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x) {
-      int phase, bt, yt, xt, nt;
-      decode_tile(P, tile, phase, bt, yt, xt, nt);
-      const int X = xt * P.TW + tx, Y = yt * P.TH + ty, b = bt * P.NB + nb;
-      const bool valid = X < P.Wg && Y < P.Hg && b < P.B;
-      const int oy = Y * P.os + (phase >> 1), ox = X * P.os + (phase & 1);
-      const size_t pix = ((size_t)b * P.Ho + oy) * P.Wo + ox;
-      const int n0 = nt * BN;
-      if (nt != cached_nt) {
-        for (int j = lane; j < BN; j += 32) {
-          const int n = n0 + j;
-          const bool ok = n < P.Cout;
-          wp[j] = ok ? P.bias[n] : 0.f;
-          wp[BN + j] = (ok && P.post_scale) ? P.post_scale[n] : 1.f;
-          wp[2 * BN + j] = (ok && P.post_shift) ? P.post_shift[n] : 0.f;
-          if constexpr (BN <= 64) {
-            if (P.gray) {
-#pragma unroll
-              for (int t = 0; t < 9; ++t) wp[(3 + t) * BN + j] = ok ? P.gray_w[t * P.Cout + n] : 0.f;
-            }
-          }
-        }
-        cached_nt = nt;
-        __syncwarp();
-      }
-      float g[9];
-      if constexpr (BN <= 64) {
-        if (P.gray) {
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
-            g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
-          }
-        }
-      }
-      mbar_wait(&tfull[as], aph, P.error_flag);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-      if (P.head == DISCO_HEAD_NONE) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-          uint32_t r[CH];
-          tmem_ld<CH>(taddr + c0, r);
-          if (valid && n0 + c0 < P.Cout) {
-            float v[CH];
-#pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(wp + c0 + j);
-              v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-              v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
-            }
-            if constexpr (BN <= 64) {
-              if (P.gray) {
-#pragma unroll
-                for (int t = 0; t < 9; ++t)
-#pragma unroll
-                  for (int j = 0; j < CH; j += 4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wp + (3 + t) * BN + c0 + j);
-                    v[j] = fmaf(g[t], wv.x, v[j]); v[j + 1] = fmaf(g[t], wv.y, v[j + 1]);
-                    v[j + 2] = fmaf(g[t], wv.z, v[j + 2]); v[j + 3] = fmaf(g[t], wv.w, v[j + 3]);
-                  }
-              }
-            }
-            if (P.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n0 + c0);
-#pragma unroll
-              for (int u = 0; u < CH / 8; ++u) {
-                const uint4 rr = __ldg(rp + u);
-                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                  v[u * 8 + 2 * j] += __low2float(h2);
-                  v[u * 8 + 2 * j + 1] += __high2float(h2);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], P.act, P.slope);
-            if (P.post_scale) {
-#pragma unroll
-              for (int j = 0; j < CH; j += 4) {
-                const float4 sv = *reinterpret_cast<const float4*>(wp + BN + c0 + j);
-                const float4 hv = *reinterpret_cast<const float4*>(wp + 2 * BN + c0 + j);
-                v[j] = fmaf(v[j], sv.x, hv.x); v[j + 1] = fmaf(v[j + 1], sv.y, hv.y);
-                v[j + 2] = fmaf(v[j + 2], sv.z, hv.z); v[j + 3] = fmaf(v[j + 3], sv.w, hv.w);
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n0 + c0);
-#pragma unroll
-            for (int u = 0; u < CH / 8; ++u) {
-              uint32_t w[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              op[u] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-        }
-      } else {
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
-        if (valid) {
-          float* outp = reinterpret_cast<float*>(P.out);
-          const size_t plane = (size_t)P.Ho * P.Wo;
-          const size_t base = (size_t)b * P.Cout * plane + (size_t)oy * P.Wo + ox;
-          if (P.head == DISCO_HEAD_SOFTMAX9) {
-            float v[9], mx = -3.4e38f, s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + wp[j]; mx = fmaxf(mx, v[j]); }
-#pragma unroll
-            for (int j = 0; j < 9; ++j) { v[j] = expf(v[j] - mx); s += v[j]; }
-            const float inv = 1.0f / s;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) outp[base + j * plane] = v[j] * inv;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + wp[j]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      if (++as == 2) { as = 0; aph ^= 1; }
-    }
+    epilogue_role<BN>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
@@ -448,6 +529,147 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resident-weight kernel for layers whose per-phase weights fit in shared memory (Cout <= 64 at full
+// resolution, heads, the 16/32-channel SpixelNet layers).  Differences from the streaming kernel above:
+//   * the weight matrix of the current phase is loaded ONCE per CTA (re-loaded only at a phase change) and
+//     every tile's MMAs read it in place -> no per-K-block weight traffic;
+//   * activation loads are grouped by filter column: one TMA box with TH+2 rows feeds the three taps
+//     dy = -1,0,+1, so a 3x3 layer costs 3 activation loads per tile instead of 9 (2.4x less L2->SMEM traffic)
+//     and 3 instead of 9 mbarrier round trips, which is what bounds N <= 64 tiles (their MMAs are short).
+// Shared-memory layout: [stages x A stage][resident weights][barriers][epilogue parameter caches].
+// ------------------------------------------------------------------------------------------------
+template <int BN, int KC>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_constant__ TcParams P) {
+  constexpr int B_BYTES = BN * KC * 2;
+  constexpr int MAX_ST = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = P.res_stages, a_stage = P.res_a_stage_bytes;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P.res_b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_ST;
+  uint64_t* tfull = bars + 2 * MAX_ST;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint64_t* bempty = bfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 1);
+  float* epi_params = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    mbar_init(bfull, 1);
+    mbar_init(bempty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_phase = P.tiles_n * P.tiles_x * P.tiles_y * P.tiles_b;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      uint32_t stage = 0, ph = 0, beph = 0;
+      int cur_phase = -1;
+      TileIter it;
+      it.init(P, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+        const int phase = it.phase, bt = it.bt;
+        if (phase != cur_phase) {
+          if (cur_phase >= 0) { mbar_wait(bempty, beph, P.error_flag); beph ^= 1; }   // MMAs of the old phase are done
+          const int nkb = P.kblocks[phase];
+          mbar_expect_tx(bfull, (uint32_t)(nkb * B_BYTES));
+          for (int kb = 0; kb < nkb; ++kb)
+            tma_load_2d(smem_b + kb * B_BYTES, &P.tmB, bfull, 0, (P.wkb_phase0[phase] + kb) * P.cout_pad);
+          cur_phase = phase;
+        }
+        const int x0 = it.xt * P.TW, y0 = it.yt * P.TH;
+        const int ns = P.nsteps[phase];
+        for (int i = 0; i < ns; ++i) {
+          const Step& sp = P.steps[phase][i];
+          mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
+          mbar_expect_tx(&full[stage], sp.bytes);
+          void* da = smem_a + stage * a_stage;
+          if (sp.mode == 0)
+            tma_load_4d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, y0 + sp.oy, bt);
+          else
+            tma_load_5d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
+          if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc<BN>();
+      const uint64_t desc_hi_lo = make_smem_desc<KC>(0);          // all fields except the start address
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      uint32_t stage = 0, ph = 0, as = 0, aph = 0, bfph = 0;
+      int cur_phase = -1;
+      TileIter it;
+      it.init(P, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+        const int phase = it.phase;
+        if (phase != cur_phase) {
+          mbar_wait(bfull, bfph, P.error_flag);
+          bfph ^= 1;
+          tc_fence_after();
+          cur_phase = phase;
+        }
+        mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        const int ns = P.nsteps[phase];
+        uint32_t acc = 0;
+        for (int i = 0; i < ns; ++i) {
+          const Step& sp = P.steps[phase][i];
+          mbar_wait(&full[stage], ph, P.error_flag);
+          tc_fence_after();
+          const uint32_t sa = a_base + stage * a_stage;
+          for (int t = 0; t < sp.ntap; ++t) {
+            const uint32_t tw = sp.tap[t];
+            const uint64_t ad = desc_hi_lo + (uint64_t)(((sa >> 4) + (tw & 0xffffu)) & 0x3fffu);
+            const uint64_t bd = desc_hi_lo + (uint64_t)(((b_base + (tw >> 16) * B_BYTES) >> 4) & 0x3fffu);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+        const int next = tile + gridDim.x;
+        if (next < P.tiles_total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);
+      }
+    }
+  } else {
+    epilogue_role<BN>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -464,7 +686,19 @@ struct Plan {
   Tap taps[4][kMaxTaps];
   int ntaps[4] = {0, 0, 0, 0};
   int kblocks[4] = {0, 0, 0, 0};
+  int wkb_phase0[4] = {0, 0, 0, 0};
+  // tile shape (phase grid): TW*TH*NB == 128
+  int Hg = 0, Wg = 0, TW = 0, TH = 0, NB = 0;
+  // resident-weight variant
+  bool resident = false;
+  Step steps[4][kMaxSteps];
+  int nsteps[4] = {0, 0, 0, 0};
+  int span[2] = {0, 0};              // extra box rows of each source's mode-0 loads
+  int res_stages = 0, res_a_stage_bytes = 0, res_b_bytes = 0, res_smem_bytes = 0;
 };
+
+int pow2_ceil_(int v) { int p = 1; while (p < v) p *= 2; return p; }
+bool g_allow_resident = true;
 
 int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
 
@@ -505,6 +739,7 @@ Plan build_plan(const disco_conv_desc* d) {
   for (int ph = 0; ph < p.n_phase; ++ph) {
     const int py = ph >> 1, px = ph & 1;
     int nt = 0;
+    p.wkb_phase0[ph] = wkb;
     for (int s = 0; s < d->n_src; ++s) {
       if (s == p.gray_src) continue;
       const disco_conv_src& src = d->src[s];
@@ -550,6 +785,87 @@ Plan build_plan(const disco_conv_desc* d) {
   }
   p.nkb_total = wkb;
   p.ok = true;
+
+  // ---- tile shape on the phase grid
+  p.Hg = d->Ho / p.os; p.Wg = d->Wo / p.os;
+  int TW = (p.Wg % 16 == 0) ? 16 : (p.Wg % 8 == 0 ? 8 : (p.Wg % 4 == 0 ? 4 : 16));
+  if (TW > pow2_ceil_(p.Wg)) TW = pow2_ceil_(p.Wg);
+  int TH = 128 / TW;
+  if (TH > pow2_ceil_(p.Hg)) TH = pow2_ceil_(p.Hg);
+  p.TW = TW; p.TH = TH; p.NB = 128 / (TW * TH);
+
+  // ---- resident-weight variant: one n-tile, whole-image tiles, weights of a phase fit in shared memory
+  int max_kb = 0;
+  for (int ph = 0; ph < p.n_phase; ++ph) max_kb = p.kblocks[ph] > max_kb ? p.kblocks[ph] : max_kb;
+  const int b_bytes = max_kb * p.BN * kc * 2;
+  if (!g_allow_resident || p.cout_pad != p.BN || p.BN > 64 || p.NB != 1 || TW < 8 || b_bytes > 112 * 1024) return p;
+  for (int s = 0; s < d->n_src; ++s) {
+    int hi = -127;
+    for (int ph = 0; ph < p.n_phase; ++ph)
+      for (int t = 0; t < p.ntaps[ph]; ++t) {
+        const Tap& tp = p.taps[ph][t];
+        if (tp.src != s || tp.mode != 0) continue;
+        // span is per (phase, ox) group; all groups of a source share one box height
+        int glo = tp.oy, ghi = tp.oy;
+        for (int u = 0; u < p.ntaps[ph]; ++u) {
+          const Tap& o = p.taps[ph][u];
+          if (o.src == s && o.mode == 0 && o.ox == tp.ox) { glo = o.oy < glo ? o.oy : glo; ghi = o.oy > ghi ? o.oy : ghi; }
+        }
+        hi = (ghi - glo) > hi ? (ghi - glo) : hi;
+      }
+    p.span[s] = hi < 0 ? 0 : hi;
+  }
+  int a_stage = TH * TW * kc * 2;
+  for (int s = 0; s < d->n_src; ++s) {
+    const int b = (TH + p.span[s]) * TW * kc * 2;
+    a_stage = b > a_stage ? b : a_stage;
+  }
+  a_stage = (a_stage + 1023) / 1024 * 1024;
+  for (int ph = 0; ph < p.n_phase; ++ph) {
+    int ns = 0;
+    bool used[kMaxTaps] = {false};
+    for (int t = 0; t < p.ntaps[ph]; ++t) {
+      if (used[t]) continue;
+      const Tap& tp = p.taps[ph][t];
+      std::vector<int> members;
+      if (tp.mode == 0) {
+        for (int u = t; u < p.ntaps[ph]; ++u) {
+          const Tap& o = p.taps[ph][u];
+          if (!used[u] && o.src == tp.src && o.mode == 0 && o.ox == tp.ox) { members.push_back(u); used[u] = true; }
+        }
+      } else {
+        members.push_back(t);
+        used[t] = true;
+      }
+      int oy_min = 127;
+      for (int u : members) oy_min = p.taps[ph][u].oy < oy_min ? p.taps[ph][u].oy : oy_min;
+      if ((int)members.size() > 3) return p;
+      for (int ch = 0; ch < tp.nchunks; ++ch) {
+        if (ns >= kMaxSteps) return p;
+        Step& st = p.steps[ph][ns++];
+        memset(&st, 0, sizeof(st));
+        st.src = tp.src; st.mode = tp.mode; st.ox = tp.ox; st.oy = (int8_t)oy_min; st.py = tp.py; st.px = tp.px;
+        st.ntap = (int8_t)members.size();
+        st.c0 = tp.c_base + ch * kc;
+        st.bytes = (uint32_t)((tp.mode == 0 ? TH + p.span[tp.src] : TH) * TW * kc * 2);
+        for (size_t i = 0; i < members.size(); ++i) {
+          const Tap& o = p.taps[ph][members[i]];
+          const uint32_t row_off = (uint32_t)((o.oy - oy_min) * TW * kc * 2) >> 4;
+          const uint32_t wblk = (uint32_t)(o.wkb0 - p.wkb_phase0[ph] + ch);
+          st.tap[i] = row_off | (wblk << 16);
+        }
+      }
+    }
+    p.nsteps[ph] = ns;
+  }
+  const int epi_bytes = 8 * (3 * p.BN + (p.BN <= 64 ? 9 * p.BN : 0)) * 4;
+  const int fixed = b_bytes + 256 + epi_bytes + 1024;
+  int stages = (225 * 1024 - fixed) / a_stage;
+  if (stages > 8) stages = 8;
+  if (stages < 3) return p;
+  p.resident = true;
+  p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_bytes;
+  p.res_smem_bytes = stages * a_stage + fixed;
   return p;
 }
 
@@ -604,6 +920,28 @@ int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
   }
   conv_tc_kernel<BN, KC><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
   return DISCO_OK;
+}
+
+template <int BN, int KC>
+int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes = smem_bytes;
+  }
+  conv_tc_res_kernel<BN, KC><<<grid, kThreads, smem_bytes, st>>>(P);
+  return DISCO_OK;
+}
+
+template <int KC>
+int launch_res_bn(int BN, const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+  switch (BN) {
+    case 16: return launch_res_cfg<16, KC>(P, grid, smem_bytes, st);
+    case 32: return launch_res_cfg<32, KC>(P, grid, smem_bytes, st);
+    case 64: return launch_res_cfg<64, KC>(P, grid, smem_bytes, st);
+  }
+  disco_set_error("conv_tc: unsupported resident BN %d", BN);
+  return DISCO_ERR_INVALID;
 }
 
 template <int KC>
@@ -665,6 +1003,12 @@ extern "C" int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float*
 }
 
 int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("DISCO_TC_RESIDENT");
+    if (e && e[0] == '0') g_allow_resident = false;
+    env_read = true;
+  }
   std::string key(reinterpret_cast<const char*>(d), sizeof(*d));
   key.append(reinterpret_cast<const char*>(&h->device), sizeof(int));
   std::lock_guard<std::mutex> lk(g_mu);
@@ -683,12 +1027,12 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     }
     P.error_flag = g_error_flag;
     P.n_phase = pl.n_phase; P.os = pl.os;
-    P.B = d->batch; P.Hg = d->Ho / pl.os; P.Wg = d->Wo / pl.os;
-    int TW = (P.Wg % 16 == 0) ? 16 : (P.Wg % 8 == 0 ? 8 : (P.Wg % 4 == 0 ? 4 : 16));
-    if (TW > pow2_ceil(P.Wg)) TW = pow2_ceil(P.Wg);
-    int TH = 128 / TW;
-    if (TH > pow2_ceil(P.Hg)) TH = pow2_ceil(P.Hg);
-    int NB = 128 / (TW * TH);
+    P.B = d->batch; P.Hg = pl.Hg; P.Wg = pl.Wg;
+    const int TW = pl.TW, TH = pl.TH, NB = pl.NB;
+    memcpy(P.steps, pl.steps, sizeof(P.steps));
+    memcpy(P.nsteps, pl.nsteps, sizeof(P.nsteps));
+    memcpy(P.wkb_phase0, pl.wkb_phase0, sizeof(P.wkb_phase0));
+    P.res_stages = pl.res_stages; P.res_a_stage_bytes = pl.res_a_stage_bytes; P.res_b_bytes = pl.res_b_bytes;
     P.TW = TW; P.TH = TH; P.NB = NB; P.tw_log2 = ilog2(TW); P.th_log2 = ilog2(TH);
     P.tiles_x = (P.Wg + TW - 1) / TW; P.tiles_y = (P.Hg + TH - 1) / TH; P.tiles_b = (P.B + NB - 1) / NB;
     P.tiles_n = pl.cout_pad / pl.BN;
@@ -719,7 +1063,7 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
       if (mode == 0) {
         cuuint64_t dims[4] = {Cc, Wd, Hd, Bd};
         cuuint64_t str[3] = {Cc * 2, Wd * Cc * 2, Hd * Wd * Cc * 2};
-        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
+        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)TW, (cuuint32_t)(pl.resident ? TH + pl.span[s] : TH), (cuuint32_t)NB};
         rc = encode(h, &P.tmA[s], const_cast<void*>(src.ptr), 4, dims, str, box, pl.KC);
       } else {
         DISCO_CHECK_ARG(src.H % 2 == 0 && src.W % 2 == 0, "conv_tc: stride-2 source must have even H, W");
@@ -742,11 +1086,20 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   }
   const Cached& c = it->second;
   int rc;
-  switch (c.plan.KC) {
-    case 64: rc = launch_bn<64>(c.plan.BN, c.params, c.grid, st); break;
-    case 32: rc = launch_bn<32>(c.plan.BN, c.params, c.grid, st); break;
-    case 16: rc = launch_bn<16>(c.plan.BN, c.params, c.grid, st); break;
-    default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
+  if (c.plan.resident) {
+    switch (c.plan.KC) {
+      case 64: rc = launch_res_bn<64>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
+      case 32: rc = launch_res_bn<32>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
+      case 16: rc = launch_res_bn<16>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
+      default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
+    }
+  } else {
+    switch (c.plan.KC) {
+      case 64: rc = launch_bn<64>(c.plan.BN, c.params, c.grid, st); break;
+      case 32: rc = launch_bn<32>(c.plan.BN, c.params, c.grid, st); break;
+      case 16: rc = launch_bn<16>(c.plan.BN, c.params, c.grid, st); break;
+      default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
+    }
   }
   if (rc != DISCO_OK) return rc;
   DISCO_LAUNCH_CHECK(h);
