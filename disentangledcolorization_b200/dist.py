@@ -1,0 +1,50 @@
+"""Batch sharding across the GPUs of one box + the single output all-gather.
+
+The forward is independent per image, so ranks take contiguous slices of the global batch with the
+weights replicated; the only exchange step is one all-gather of `pred_colors` (NCCL over
+NVLink/NVSwitch on GPUs, gloo in the CPU tests).  To match a single-process run of the reference
+(whose k-means init consumes `np.random.choice` once per image in batch order), every rank draws the
+init index sets of ALL images and keeps its own slice (`sharded_init_draws`).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch, world_size, rank):
+    """Contiguous [lo, hi) slice of rank `rank`; the first (global_batch % world_size) ranks get one extra."""
+    base, extra = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sharded_init_draws(global_batch, n_tokens, n_clusters, world_size, rank):
+    """np.random.choice(S, K, replace=False) for every image of the GLOBAL batch (same stream on every rank);
+    returns this rank's rows as int32 (hi-lo, K)."""
+    allidx = np.stack([np.random.choice(n_tokens, n_clusters, replace=False) for _ in range(global_batch)])
+    lo, hi = shard_bounds(global_batch, world_size, rank)
+    return allidx[lo:hi].astype(np.int32)
+
+
+def gather_outputs(local, global_batch=None, group=None):
+    """All-gather of a per-rank (b_r, ...) tensor into (sum b_r, ...), in rank order.  One collective when the
+    shards are equal (the benchmark configuration); padded all-gather otherwise."""
+    if not dist.is_available() or not dist.is_initialized():
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if global_batch is None:
+        global_batch = local.shape[0] * world
+    sizes = [shard_bounds(global_batch, world, r)[1] - shard_bounds(global_batch, world, r)[0] for r in range(world)]
+    assert sizes[rank] == local.shape[0], "local shard does not match shard_bounds()"
+    local = local.contiguous()
+    if len(set(sizes)) == 1:
+        out = local.new_empty((global_batch,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    mx = max(sizes)
+    padded = local.new_zeros((mx,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    buf = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    return torch.cat([buf[r * mx: r * mx + sizes[r]] for r in range(world)], 0)

@@ -283,7 +283,7 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, gray, ab, sampled_T=0, hint_mask=None, sync_rng=True):
+    def forward(self, gray, ab, sampled_T=0, hint_mask=None, sync_rng=True, init_idx=None):
         """Returns the reference 6-tuple (pal_logit, ref_logit, pred_colors, affinity_map, spix_colors, hint_mask)."""
         self._resolve_rng()
         if gray.dim() != 4 or gray.shape[1] != 1:
@@ -317,8 +317,11 @@ class Engine:
 
         if hint_mask is None:                                                           # model.py:140-141
             K = self.n_clusters
-            for n in range(B):
-                tok["init_idx_host"][n] = torch.from_numpy(np.random.choice(S, K, replace=False).astype(np.int32))
+            if init_idx is not None:                 # sharded runs: rows drawn for the global batch (dist.py)
+                tok["init_idx_host"].copy_(torch.as_tensor(np.asarray(init_idx, dtype=np.int32)).view(B, K))
+            else:
+                for n in range(B):
+                    tok["init_idx_host"][n] = torch.from_numpy(np.random.choice(S, K, replace=False).astype(np.int32))
             state = torch.get_rng_state()
             tok["draws_host"].copy_(torch.randint(S, (N_DRAWS,)).to(torch.int32))
             torch.set_rng_state(state)

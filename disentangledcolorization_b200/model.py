@@ -118,12 +118,13 @@ class AnchorColorProb(nn.Module):
             self._engine_key = key
         return self._engine
 
-    def forward(self, input_grays, input_colors, test_mode=False, sampled_T=0, hint_mask=None):
+    def forward(self, input_grays, input_colors, test_mode=False, sampled_T=0, hint_mask=None, init_idx=None):
         """Same contract as the reference forward (models/model.py:103,199).  `hint_mask` (extension):
-        inject anchor sites instead of running k-means."""
+        inject anchor sites instead of running k-means; `init_idx` (extension): k-means init rows for this
+        shard when the batch is split over ranks (dist.sharded_init_draws)."""
         if not test_mode:
             raise _lib.DiscoError("the training branch (test_mode=False) is not built; SURVEY.md section 8f N3")
         if self.training:
             raise _lib.DiscoError("call model.eval() first: only the eval-mode forward is built")
         return self.engine(input_grays.device).forward(input_grays, input_colors, sampled_T=sampled_T,
-                                                       hint_mask=hint_mask)
+                                                       hint_mask=hint_mask, init_idx=init_idx)
