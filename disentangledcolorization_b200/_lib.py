@@ -17,7 +17,8 @@ CONV3, DECONV4 = 0, 1
 EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
            "disco_reset_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
-           "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights"]
+           "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
+           "disco_debug_timeline"]
 
 
 class ConvSrc(C.Structure):

@@ -90,6 +90,8 @@ struct TcParams {
   const float* gray;
   const float* gray_w;        // [9][Cout]
   int32_t* error_flag;
+  int32_t dbg_mode;           // experiments: 1 = epilogue skips TMEM loads + stores, 2 = skips stores only, 3 = producer loads once
+  long long* dbg;             // optional timeline buffer (DISCO_TC_DEBUG=1): [role][tile][slot] clock64 stamps of CTA 0
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -154,6 +156,14 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float lds32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -161,6 +171,13 @@ __device__ __forceinline__ float lds32(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+constexpr int kDbgTiles = 48, kDbgSlots = 8;
+__device__ __forceinline__ void dbg_stamp(const TcParams& P, int role, int tile_i, int slot) {
+#ifdef DISCO_TC_TIMELINE   // compile-time only: the checks cost issue slots in the single-thread role loops
+  if (P.dbg && blockIdx.x == 0 && tile_i < kDbgTiles && slot < kDbgSlots)
+    P.dbg[(role * kDbgTiles + tile_i) * kDbgSlots + slot] = clock64();
+#endif
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -234,8 +251,9 @@ struct Cfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // per-epilogue-warp parameter cache: bias | post_scale | post_shift (+ 9 x fp32 L-channel weights when BN <= 64)
-  static constexpr int EPI_FLOATS = 3 * BN + (BN <= 64 ? 9 * BN : 0);
-  static constexpr int EPI_BYTES = 8 * EPI_FLOATS * 4;
+  static constexpr int EPI_COLS = BN >= 32 ? BN / 2 : BN;
+  static constexpr int EPI_FLOATS = 3 * EPI_COLS + (BN <= 64 ? 9 * EPI_COLS : 0);
+  static constexpr int EPI_BYTES = 8 * EPI_FLOATS * 4 + 8 * 2048;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
@@ -256,13 +274,14 @@ struct TileIter {
     dy = t % P.tiles_y; t /= P.tiles_y;
     db = t % P.tiles_b; dp = t / P.tiles_b;
   }
-  __device__ __forceinline__ void next(const TcParams& P) {
-    nt += dn; int c = nt >= P.tiles_n; nt -= c ? P.tiles_n : 0;
-    xt += dx + c; c = xt >= P.tiles_x; xt -= c ? P.tiles_x : 0;
-    yt += dy + c; c = yt >= P.tiles_y; yt -= c ? P.tiles_y : 0;
-    bt += db + c; c = bt >= P.tiles_b; bt -= c ? P.tiles_b : 0;
+  __device__ __forceinline__ void next(int tn, int tX, int tY, int tB) {
+    nt += dn; int c = nt >= tn; nt -= c ? tn : 0;
+    xt += dx + c; c = xt >= tX; xt -= c ? tX : 0;
+    yt += dy + c; c = yt >= tY; yt -= c ? tY : 0;
+    bt += db + c; c = bt >= tB; bt -= c ? tB : 0;
     phase += dp + c;
   }
+  __device__ __forceinline__ void next(const TcParams& P) { next(P.tiles_n, P.tiles_x, P.tiles_y, P.tiles_b); }
 };
 
 __device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& phase, int& bt, int& yt, int& xt, int& nt) {
@@ -280,39 +299,51 @@ __device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& ph
 template <int BN>
 __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                               float* epi_params, int warp, int lane) {
-  constexpr int EPI_FLOATS = 3 * BN + (BN <= 64 ? 9 * BN : 0);
+  constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
   constexpr int NHALF = BN >= 32 ? 2 : 1;       // column halves (one per warp of a lane quarter)
   constexpr int COLS = BN / NHALF;              // columns this warp owns
+  constexpr int EPI_FLOATS = 3 * COLS + (BN <= 64 ? 9 * COLS : 0);   // per-warp cache: bias|scale|shift(|9 gray taps)
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
   const bool active = half < NHALF;
   const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
   const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
   const uint32_t wp = smem_u32(epi_params + (warp - 2) * EPI_FLOATS);   // this warp's private parameter cache
+  const uint32_t stg = smem_u32(epi_params + 8 * EPI_FLOATS) + (warp - 2) * EPI_STAGE;   // output staging patch
   const int col0 = half * COLS;
+  // hot parameters hoisted out of the tile loop (the parameter block is several KB: re-reading it through the
+  // constant cache inside the loop stalls on misses)
+  const int pTW = P.TW, pTH = P.TH, pNB = P.NB, pWg = P.Wg, pHg = P.Hg, pB = P.B, pos = P.os, pHo = P.Ho, pWo = P.Wo;
+  const int pCout = P.Cout, pact = P.act, phead = P.head, ptotal = P.tiles_total;
+  const float pslope = P.slope;
+  const bool has_post = P.post_scale != nullptr;
+  const __nv_bfloat16* const pres = P.residual;
+  __nv_bfloat16* const pout = reinterpret_cast<__nv_bfloat16*>(P.out);
+  int32_t* const perr = P.error_flag;
   int cached_nt = -1;
   uint32_t as = 0, aph = 0;
   TileIter it;
   it.init(P, blockIdx.x, gridDim.x);
-  for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+  const int tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
+  for (int tile = blockIdx.x; tile < ptotal; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
     const int phase = it.phase, nt = it.nt;
-    const int X = it.xt * P.TW + tx, Y = it.yt * P.TH + ty, b = it.bt * P.NB + nb;
-    const bool valid = active && X < P.Wg && Y < P.Hg && b < P.B;
-    const int oy = Y * P.os + (phase >> 1), ox = X * P.os + (phase & 1);
-    const size_t pix = ((size_t)b * P.Ho + oy) * P.Wo + ox;
+    const int X = it.xt * pTW + tx, Y = it.yt * pTH + ty, b = it.bt * pNB + nb;
+    const bool valid = active && X < pWg && Y < pHg && b < pB;
+    const int oy = Y * pos + (phase >> 1), ox = X * pos + (phase & 1);
+    const size_t pix = ((size_t)b * pHo + oy) * pWo + ox;
     const int n0 = nt * BN;
     if (nt != cached_nt) {
-      for (int j = lane; j < BN; j += 32) {
-        const int n = n0 + j;
-        const bool ok = n < P.Cout;
+      for (int j = lane; j < COLS; j += 32) {
+        const int n = n0 + col0 + j;
+        const bool ok = n < pCout;
         sts32(wp + 4 * j, ok ? P.bias[n] : 0.f);
-        sts32(wp + 4 * (BN + j), (ok && P.post_scale) ? P.post_scale[n] : 1.f);
-        sts32(wp + 4 * (2 * BN + j), (ok && P.post_shift) ? P.post_shift[n] : 0.f);
+        sts32(wp + 4 * (COLS + j), (ok && P.post_scale) ? P.post_scale[n] : 1.f);
+        sts32(wp + 4 * (2 * COLS + j), (ok && P.post_shift) ? P.post_shift[n] : 0.f);
         if constexpr (BN <= 64) {
           if (P.gray) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) sts32(wp + 4 * ((3 + t) * BN + j), ok ? P.gray_w[t * P.Cout + n] : 0.f);
+            for (int t = 0; t < 9; ++t) sts32(wp + 4 * ((3 + t) * COLS + j), ok ? P.gray_w[t * pCout + n] : 0.f);
           }
         }
       }
@@ -325,24 +356,26 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int gy = oy + t / 3 - 1, gx = ox + t % 3 - 1;
-          g[t] = (valid && gy >= 0 && gy < P.Ho && gx >= 0 && gx < P.Wo) ? P.gray[((size_t)b * P.Ho + gy) * P.Wo + gx] : 0.f;
+          g[t] = (valid && gy >= 0 && gy < pHo && gx >= 0 && gx < pWo) ? P.gray[((size_t)b * pHo + gy) * pWo + gx] : 0.f;
         }
       }
     }
-    mbar_wait(&tfull[as], aph, P.error_flag);
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 0);
+    mbar_wait(&tfull[as], aph, perr);
     tc_fence_after();
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 1);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-    if (P.head == DISCO_HEAD_NONE) {
-      if (active) {
+    if (phead == DISCO_HEAD_NONE) {
+      if (active && P.dbg_mode != 1) {
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + COLS; c0 += CH) {
           uint32_t r[CH];
           tmem_ld<CH>(taddr + c0, r);
-          if (valid && n0 + c0 < P.Cout) {
+          if (valid && n0 + c0 < pCout) {
             float v[CH];
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              const float4 bv = lds128(wp + 4 * (c0 + j));
+              const float4 bv = lds128(wp + 4 * (c0 - col0 + j));
               v[j] = __uint_as_float(r[j]) + bv.x; v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
               v[j + 2] = __uint_as_float(r[j + 2]) + bv.z; v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
             }
@@ -352,14 +385,14 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
                 for (int t = 0; t < 9; ++t)
 #pragma unroll
                   for (int j = 0; j < CH; j += 4) {
-                    const float4 wv = lds128(wp + 4 * ((3 + t) * BN + c0 + j));
+                    const float4 wv = lds128(wp + 4 * ((3 + t) * COLS + c0 - col0 + j));
                     v[j] = fmaf(g[t], wv.x, v[j]); v[j + 1] = fmaf(g[t], wv.y, v[j + 1]);
                     v[j + 2] = fmaf(g[t], wv.z, v[j + 2]); v[j + 3] = fmaf(g[t], wv.w, v[j + 3]);
                   }
               }
             }
-            if (P.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix * P.Cout + n0 + c0);
+            if (pres) {
+              const uint4* rp = reinterpret_cast<const uint4*>(pres + pix * pCout + n0 + c0);
 #pragma unroll
               for (int u = 0; u < CH / 8; ++u) {
                 const uint4 rr = __ldg(rp + u);
@@ -372,33 +405,62 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
                 }
               }
             }
-            if (P.act == DISCO_ACT_RELU) {
+            if (pact == DISCO_ACT_RELU) {
 #pragma unroll
               for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (P.act == DISCO_ACT_LRELU) {
+            } else if (pact == DISCO_ACT_LRELU) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], v[j] * P.slope);   // slope in [0,1)
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], v[j] * pslope);   // slope in [0,1)
             }
-            if (P.post_scale) {
+            if (has_post) {
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
-                const float4 sv = lds128(wp + 4 * (BN + c0 + j));
-                const float4 hv = lds128(wp + 4 * (2 * BN + c0 + j));
+                const float4 sv = lds128(wp + 4 * (COLS + c0 - col0 + j));
+                const float4 hv = lds128(wp + 4 * (2 * COLS + c0 - col0 + j));
                 v[j] = fmaf(v[j], sv.x, hv.x); v[j + 1] = fmaf(v[j + 1], sv.y, hv.y);
                 v[j + 2] = fmaf(v[j + 2], sv.z, hv.z); v[j + 3] = fmaf(v[j + 3], sv.w, hv.w);
               }
             }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.Cout + n0 + c0);
+            if constexpr (CH == 16) {
+              uint4* op = reinterpret_cast<uint4*>(pout + pix * pCout + n0 + c0);
 #pragma unroll
-            for (int u = 0; u < CH / 8; ++u) {
-              uint32_t w[4];
+              for (int u = 0; u < 2; ++u) {
+                uint32_t w[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                op[u] = make_uint4(w[0], w[1], w[2], w[3]);
               }
-              op[u] = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              // stage this lane's 64 B (32 channels) in the warp's patch, XOR-swizzled on the 16-byte piece index
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u * 8 + 2 * j], v[u * 8 + 2 * j + 1]);
+                  w[j] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                sts128(stg + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
+              }
             }
+          }
+          if constexpr (CH == 32) {
+            // coalesced write-out: 4 lanes cover one pixel's 64 B, a warp instruction writes 8 pixels x 64 B
+            __syncwarp();
+            const bool chunk_ok = n0 + c0 < pCout;
+            const __nv_bfloat16* mybase = pout + pix * pCout + n0 + c0;
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+              const int p = (lane >> 2) + 8 * i2, piece = lane & 3;
+              const unsigned long long a = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)mybase, p);
+              const int ok = __shfl_sync(0xffffffffu, (int)valid, p);
+              const uint4 val = lds128u(stg + p * 64 + ((piece ^ ((p >> 1) & 3)) << 4));
+              if (ok && chunk_ok && P.dbg_mode != 2) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a) + piece * 16) = val;
+            }
+            __syncwarp();
           }
         }
       }
@@ -407,9 +469,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
       tmem_ld16(taddr, r);
       if (valid) {
         float* outp = reinterpret_cast<float*>(P.out);
-        const size_t plane = (size_t)P.Ho * P.Wo;
-        const size_t base = (size_t)b * P.Cout * plane + (size_t)oy * P.Wo + ox;
-        if (P.head == DISCO_HEAD_SOFTMAX9) {
+        const size_t plane = (size_t)pHo * pWo;
+        const size_t base = (size_t)b * pCout * plane + (size_t)oy * pWo + ox;
+        if (phead == DISCO_HEAD_SOFTMAX9) {
           float v[9], mx = -3.4e38f, s = 0.f;
 #pragma unroll
           for (int j = 0; j < 9; ++j) { v[j] = __uint_as_float(r[j]) + lds32(wp + 4 * j); mx = fmaxf(mx, v[j]); }
@@ -427,6 +489,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty[as]);
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 2);
     if (++as == 2) { as = 0; aph ^= 1; }
   }
 }
@@ -610,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
             tma_load_4d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, y0 + sp.oy, bt);
           else
             tma_load_5d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
+          dbg_stamp(P, 0, (tile - blockIdx.x) / gridDim.x, i);
           if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
         }
       }
@@ -632,8 +696,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
           tc_fence_after();
           cur_phase = phase;
         }
+        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 0);
         mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
         tc_fence_after();
+        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 1);
         const uint32_t d_tmem = tmem_base + as * BN;
         const int ns = P.nsteps[phase];
         uint32_t acc = 0;
@@ -641,6 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
           const Step& sp = P.steps[phase][i];
           mbar_wait(&full[stage], ph, P.error_flag);
           tc_fence_after();
+          dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 2 + i);
           const uint32_t sa = a_base + stage * a_stage;
           for (int t = 0; t < sp.ntap; ++t) {
             const uint32_t tw = sp.tap[t];
@@ -656,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
           if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
         }
         umma_commit(&tfull[as]);
+        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 7);
         if (++as == 2) { as = 0; aph ^= 1; }
         const int next = tile + gridDim.x;
         if (next < P.tiles_total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);
@@ -858,7 +926,8 @@ Plan build_plan(const disco_conv_desc* d) {
     }
     p.nsteps[ph] = ns;
   }
-  const int epi_bytes = 8 * (3 * p.BN + (p.BN <= 64 ? 9 * p.BN : 0)) * 4;
+  const int epi_cols = p.BN >= 32 ? p.BN / 2 : p.BN;
+  const int epi_bytes = 8 * (3 * epi_cols + (p.BN <= 64 ? 9 * epi_cols : 0)) * 4 + 8 * 2048;
   const int fixed = b_bytes + 256 + epi_bytes + 1024;
   int stages = (225 * 1024 - fixed) / a_stage;
   if (stages > 8) stages = 8;
@@ -909,6 +978,7 @@ struct Cached {
 std::mutex g_mu;
 std::map<std::string, Cached> g_cache;
 int32_t* g_error_flag = nullptr;
+long long* g_dbg = nullptr;
 
 template <int BN, int KC>
 int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
@@ -1002,6 +1072,14 @@ extern "C" int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float*
   return DISCO_OK;
 }
 
+// debug: copies the timeline of the last DISCO_TC_DEBUG launch to `out` (4*48*8 int64); returns element count
+extern "C" int disco_debug_timeline(long long* out) {
+  if (!g_dbg) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_dbg, sizeof(long long) * 4 * kDbgTiles * kDbgSlots, cudaMemcpyDeviceToHost);
+  return 4 * kDbgTiles * kDbgSlots;
+}
+
 int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   static bool env_read = false;
   if (!env_read) {
@@ -1026,6 +1104,14 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
       DISCO_CUDA(cudaMemset(g_error_flag, 0, sizeof(int32_t)));
     }
     P.error_flag = g_error_flag;
+    if (getenv("DISCO_TC_MODE")) P.dbg_mode = atoi(getenv("DISCO_TC_MODE"));
+    if (getenv("DISCO_TC_DEBUG")) {
+      if (!g_dbg) {
+        DISCO_CUDA(cudaMalloc(&g_dbg, sizeof(long long) * 4 * kDbgTiles * kDbgSlots));
+      }
+      DISCO_CUDA(cudaMemset(g_dbg, 0, sizeof(long long) * 4 * kDbgTiles * kDbgSlots));
+      P.dbg = g_dbg;
+    }
     P.n_phase = pl.n_phase; P.os = pl.os;
     P.B = d->batch; P.Hg = pl.Hg; P.Wg = pl.Wg;
     const int TW = pl.TW, TH = pl.TH, NB = pl.NB;

@@ -103,6 +103,8 @@ int disco_set_tensor_core(disco_handle* h, int enable);
 int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d);
 int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d);
 int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float* w_f32_host, uint16_t* w_bf16_host);
+/* debug aid: per-role clock64 timeline of CTA 0 of the last tensor-core launch made with DISCO_TC_DEBUG=1 */
+int disco_debug_timeline(long long* out_host);
 
 /* ---------------------------------------------------------------------------------------------
  * Super-pixel pooling.  Replaces basic.poolfeat (models/basic.py:274-324) applied to
