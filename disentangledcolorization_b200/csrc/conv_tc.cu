@@ -58,18 +58,20 @@ struct Step {
   int8_t src, mode, ox, oy, py, px, ntap, pad;
   int32_t c0;          // inner-dimension start coordinate (channel chunk, + px*C for the stride-2 view)
   uint32_t bytes;      // bytes the load delivers
-  uint32_t tap[3];     // (A start offset in bytes >> 4) | (resident weight block index << 16)
+  uint32_t a_sbo16;    // byte distance between 8-row groups of the A operand, >> 4 (halo tiles: (TW+2) pixels)
+  uint32_t tap[9];     // (A start offset in bytes >> 4) | (resident weight block index << 16)
 };
 constexpr int kMaxSteps = 16;
 
 struct TcParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
-  Step steps[4][kMaxSteps];
+  const uint32_t* tables;     // device copy of {Step steps[4][kMaxSteps]; Tap taps[4][kMaxTaps]} (staged to smem at start;
+                              // keeping them out of the parameter block keeps it < 1 KB -> constant-cache resident)
   int32_t nsteps[4];
   int32_t wkb_phase0[4];      // first weight K-block of each phase in the packed matrix
   int32_t res_stages, res_a_stage_bytes, res_b_bytes;
-  Tap taps[4][kMaxTaps];
+  int32_t halo_bo_mask;       // 0: A descriptors carry base_offset 0; else mask applied to (start_addr >> 7)
   int32_t ntaps[4];
   int32_t kblocks[4];         // K-blocks per phase
   int32_t n_phase, os;        // phases (1 | 4), output stride of a phase grid (1 | 2)
@@ -284,13 +286,6 @@ struct TileIter {
   __device__ __forceinline__ void next(const TcParams& P) { next(P.tiles_n, P.tiles_x, P.tiles_y, P.tiles_b); }
 };
 
-__device__ __forceinline__ void decode_tile(const TcParams& P, int tile, int& phase, int& bt, int& yt, int& xt, int& nt) {
-  nt = tile % P.tiles_n; tile /= P.tiles_n;
-  xt = tile % P.tiles_x; tile /= P.tiles_x;
-  yt = tile % P.tiles_y; tile /= P.tiles_y;
-  bt = tile % P.tiles_b; tile /= P.tiles_b;
-  phase = tile;
-}
 
 // ------------------------------------------------------------------------------------------------ epilogue
 // Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
@@ -510,6 +505,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   float* epi_params = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ Tap s_taps[4 * kMaxTaps];
+  {
+    const uint32_t* src = P.tables + sizeof(Step) * 4 * kMaxSteps / 4;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_taps);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tap) * 4 * kMaxTaps / 4); i += blockDim.x) dst[i] = src[i];
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int x0 = it.xt * P.TW, y0 = it.yt * P.TH, b0 = it.bt * P.NB;
         const int ntap = P.ntaps[phase];
         for (int t = 0; t < ntap; ++t) {
-          const Tap tp = P.taps[phase][t];
+          const Tap tp = s_taps[phase * kMaxTaps + t];
           for (int ch = 0; ch < tp.nchunks; ++ch) {
             mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
             mbar_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -558,26 +559,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===================================================================== MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc<BN>();
+      constexpr int NK = KC / 16;
+      const uint64_t desc0 = make_smem_desc<KC>(0);
+      const uint32_t a_base16 = smem_u32(smem_a) >> 4, b_base16 = smem_u32(smem_b) >> 4;
       uint32_t stage = 0, ph = 0, as = 0, aph = 0;
+      const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
+      const int kbs[4] = {P.kblocks[0], P.kblocks[1], P.kblocks[2], P.kblocks[3]};
+      int32_t* const perr = P.error_flag;
       TileIter it;
       it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
-        const int phase = it.phase;
-        const int nkb = P.kblocks[phase];
-        mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
+        const int nkb = kbs[it.phase];
+        mbar_wait(&tempty[as], aph ^ 1, perr);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], ph, P.error_flag);
+          mbar_wait(&full[stage], ph, perr);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+          const uint64_t ad = desc0 + (uint64_t)((a_base16 + stage * (C::A_BYTES >> 4)) & 0x3fffu);
+          const uint64_t bd = desc0 + (uint64_t)((b_base16 + stage * (C::B_BYTES >> 4)) & 0x3fffu);
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            umma_bf16(d_tmem, make_smem_desc<KC>(sa + k * 32), make_smem_desc<KC>(sb + k * 32), idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < NK; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
-          if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+          if (++stage == (uint32_t)C::STAGES) { stage = 0; ph ^= 1; }
         }
         umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -624,6 +628,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 1);
   float* epi_params = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // step tables in shared memory: indexed reads of the multi-KB kernel-parameter block go through the constant
+  // cache and cost ~60+ dependent cycles per tap inside the single-thread issue loops
+  __shared__ Step s_steps[4 * kMaxSteps];
+  __shared__ int s_nsteps[4];
+  {
+    const uint32_t* src = P.tables;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_steps);
+    for (int i = threadIdx.x; i < (int)(sizeof(Step) * 4 * kMaxSteps / 4); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 4) s_nsteps[threadIdx.x] = P.nsteps[threadIdx.x];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -663,9 +677,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
           cur_phase = phase;
         }
         const int x0 = it.xt * P.TW, y0 = it.yt * P.TH;
-        const int ns = P.nsteps[phase];
+        const int ns = s_nsteps[phase];
         for (int i = 0; i < ns; ++i) {
-          const Step& sp = P.steps[phase][i];
+          const Step& sp = s_steps[phase * kMaxSteps + i];
           mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
           mbar_expect_tx(&full[stage], sp.bytes);
           void* da = smem_a + stage * a_stage;
@@ -682,51 +696,67 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
     // ===================================================================== MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = instr_desc<BN>();
+      constexpr int NK = KC / 16;
       const uint64_t desc_hi_lo = make_smem_desc<KC>(0);          // all fields except the start address
       const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      const uint32_t desc_hi_fixed = (uint32_t)(desc_hi_lo >> 32) & ~0x3fffu;   // version + swizzle mode
+      const uint32_t b_hi = (uint32_t)(desc_hi_lo >> 32);
+      const uint32_t b_lo0 = (b_base >> 4) | 0x10000u;
       uint32_t stage = 0, ph = 0, as = 0, aph = 0, bfph = 0;
       int cur_phase = -1;
+      const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
+      int32_t* const perr = P.error_flag;
       TileIter it;
       it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
         const int phase = it.phase;
         if (phase != cur_phase) {
-          mbar_wait(bfull, bfph, P.error_flag);
+          mbar_wait(bfull, bfph, perr);
           bfph ^= 1;
-          tc_fence_after();
           cur_phase = phase;
         }
         dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 0);
-        mbar_wait(&tempty[as], aph ^ 1, P.error_flag);
+        mbar_wait(&tempty[as], aph ^ 1, perr);
         tc_fence_after();
         dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 1);
         const uint32_t d_tmem = tmem_base + as * BN;
-        const int ns = P.nsteps[phase];
+        const int ns = s_nsteps[phase];
         uint32_t acc = 0;
         for (int i = 0; i < ns; ++i) {
-          const Step& sp = P.steps[phase][i];
-          mbar_wait(&full[stage], ph, P.error_flag);
+          const Step& sp = s_steps[phase * kMaxSteps + i];
+          mbar_wait(&full[stage], ph, perr);
           tc_fence_after();
           dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 2 + i);
-          const uint32_t sa = a_base + stage * a_stage;
-          for (int t = 0; t < sp.ntap; ++t) {
-            const uint32_t tw = sp.tap[t];
-            const uint64_t ad = desc_hi_lo + (uint64_t)(((sa >> 4) + (tw & 0xffffu)) & 0x3fffu);
-            const uint64_t bd = desc_hi_lo + (uint64_t)(((b_base + (tw >> 16) * B_BYTES) >> 4) & 0x3fffu);
+          // Descriptors are assembled from 32-bit halves with one add per tap: the hi words (stride, version,
+          // swizzle mode) are loop invariants, the lo word is (smem address >> 4) | LBO.
+          const uint32_t sa_lo = ((a_base + stage * a_stage) >> 4) | 0x10000u;
+          const uint32_t a_hi = (sp.a_sbo16 & 0x3fffu) | desc_hi_fixed;
+          const int ntap = sp.ntap;
+          uint32_t nstage = stage + 1, nph = ph;
+          if (nstage == (uint32_t)stages) { nstage = 0; nph ^= 1; }
+          uint32_t tw[9];
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, acc);
-              acc = 1;
+          for (int t = 0; t < 9; ++t) tw[t] = sp.tap[t];
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < ntap) {
+              const uint32_t a_lo = sa_lo + (tw[t] & 0xffffu);
+              const uint32_t b_lo = b_lo0 + (tw[t] >> 16) * (uint32_t)(B_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < NK; ++k) {
+                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
+                acc = 1;
+              }
             }
           }
           umma_commit(&empty[stage]);
-          if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
+          stage = nstage; ph = nph;
         }
         umma_commit(&tfull[as]);
         dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 7);
         if (++as == 2) { as = 0; aph ^= 1; }
         const int next = tile + gridDim.x;
-        if (next < P.tiles_total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);
+        if (next < total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);
       }
     }
   } else {
@@ -762,11 +792,15 @@ struct Plan {
   Step steps[4][kMaxSteps];
   int nsteps[4] = {0, 0, 0, 0};
   int span[2] = {0, 0};              // extra box rows of each source's mode-0 loads
+  int spanx[2] = {0, 0};             // extra box columns (halo mode)
+  bool halo = false;
   int res_stages = 0, res_a_stage_bytes = 0, res_b_bytes = 0, res_smem_bytes = 0;
 };
 
 int pow2_ceil_(int v) { int p = 1; while (p < v) p *= 2; return p; }
 bool g_allow_resident = true;
+int g_halo_mode = 1;                 // 0 off, 1 halo tiles (descriptor base_offset 0: the hardware swizzle is a function of
+                                     // the absolute smem address -- verified on B200), 2 = experiment: base_offset from addr bits (wrong)
 
 int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
 
@@ -867,25 +901,33 @@ Plan build_plan(const disco_conv_desc* d) {
   for (int ph = 0; ph < p.n_phase; ++ph) max_kb = p.kblocks[ph] > max_kb ? p.kblocks[ph] : max_kb;
   const int b_bytes = max_kb * p.BN * kc * 2;
   if (!g_allow_resident || p.cout_pad != p.BN || p.BN > 64 || p.NB != 1 || TW < 8 || b_bytes > 112 * 1024) return p;
-  for (int s = 0; s < d->n_src; ++s) {
-    int hi = -127;
-    for (int ph = 0; ph < p.n_phase; ++ph)
+  // halo mode: 8-pixel-wide tiles so that an 8-row MMA group is 8 consecutive pixels of one image row; ONE box
+  // with the full (TW+2) x (TH+2) halo then serves all taps of a source (A descriptors start at arbitrary pixel
+  // offsets inside the box; the swizzle phase is carried by the address / descriptor base offset)
+  const bool halo = g_halo_mode != 0 && p.Wg % 8 == 0 && pow2_ceil_(p.Hg) >= 16;
+  if (halo) { TW = 8; TH = 16; p.TW = TW; p.TH = TH; p.NB = 1; }
+  p.halo = halo;
+  // per-source extents of the mode-0 tap offsets (box = tile + span)
+  int omin_y[4][2], omin_x[4][2];
+  for (int s = 0; s < 2; ++s) { p.span[s] = 0; p.spanx[s] = 0; }
+  for (int ph = 0; ph < p.n_phase; ++ph)
+    for (int s = 0; s < d->n_src; ++s) {
+      int ylo = 127, yhi = -127, xlo = 127, xhi = -127;
       for (int t = 0; t < p.ntaps[ph]; ++t) {
         const Tap& tp = p.taps[ph][t];
         if (tp.src != s || tp.mode != 0) continue;
-        // span is per (phase, ox) group; all groups of a source share one box height
-        int glo = tp.oy, ghi = tp.oy;
-        for (int u = 0; u < p.ntaps[ph]; ++u) {
-          const Tap& o = p.taps[ph][u];
-          if (o.src == s && o.mode == 0 && o.ox == tp.ox) { glo = o.oy < glo ? o.oy : glo; ghi = o.oy > ghi ? o.oy : ghi; }
-        }
-        hi = (ghi - glo) > hi ? (ghi - glo) : hi;
+        ylo = tp.oy < ylo ? tp.oy : ylo; yhi = tp.oy > yhi ? tp.oy : yhi;
+        xlo = tp.ox < xlo ? tp.ox : xlo; xhi = tp.ox > xhi ? tp.ox : xhi;
       }
-    p.span[s] = hi < 0 ? 0 : hi;
-  }
+      omin_y[ph][s] = ylo; omin_x[ph][s] = xlo;
+      if (yhi >= ylo) {
+        p.span[s] = (yhi - ylo) > p.span[s] ? (yhi - ylo) : p.span[s];
+        if (halo) p.spanx[s] = (xhi - xlo) > p.spanx[s] ? (xhi - xlo) : p.spanx[s];
+      }
+    }
   int a_stage = TH * TW * kc * 2;
   for (int s = 0; s < d->n_src; ++s) {
-    const int b = (TH + p.span[s]) * TW * kc * 2;
+    const int b = (TH + p.span[s]) * (TW + p.spanx[s]) * kc * 2;
     a_stage = b > a_stage ? b : a_stage;
   }
   a_stage = (a_stage + 1023) / 1024 * 1024;
@@ -899,28 +941,30 @@ Plan build_plan(const disco_conv_desc* d) {
       if (tp.mode == 0) {
         for (int u = t; u < p.ntaps[ph]; ++u) {
           const Tap& o = p.taps[ph][u];
-          if (!used[u] && o.src == tp.src && o.mode == 0 && o.ox == tp.ox) { members.push_back(u); used[u] = true; }
+          if (!used[u] && o.src == tp.src && o.mode == 0 && (halo || o.ox == tp.ox)) { members.push_back(u); used[u] = true; }
         }
       } else {
         members.push_back(t);
         used[t] = true;
       }
-      int oy_min = 127;
-      for (int u : members) oy_min = p.taps[ph][u].oy < oy_min ? p.taps[ph][u].oy : oy_min;
-      if ((int)members.size() > 3) return p;
+      if ((int)members.size() > 9) return p;
+      const int oy_min = tp.mode == 0 ? omin_y[ph][tp.src] : tp.oy;
+      const int ox_min = (tp.mode == 0 && halo) ? omin_x[ph][tp.src] : tp.ox;
+      const int row_px = (tp.mode == 0) ? TW + p.spanx[tp.src] : TW;        // pixels per box row
       for (int ch = 0; ch < tp.nchunks; ++ch) {
         if (ns >= kMaxSteps) return p;
         Step& st = p.steps[ph][ns++];
         memset(&st, 0, sizeof(st));
-        st.src = tp.src; st.mode = tp.mode; st.ox = tp.ox; st.oy = (int8_t)oy_min; st.py = tp.py; st.px = tp.px;
+        st.src = tp.src; st.mode = tp.mode; st.ox = (int8_t)ox_min; st.oy = (int8_t)oy_min; st.py = tp.py; st.px = tp.px;
         st.ntap = (int8_t)members.size();
         st.c0 = tp.c_base + ch * kc;
-        st.bytes = (uint32_t)((tp.mode == 0 ? TH + p.span[tp.src] : TH) * TW * kc * 2);
+        st.bytes = (uint32_t)((tp.mode == 0 ? (TH + p.span[tp.src]) * row_px : TH * TW) * kc * 2);
+        st.a_sbo16 = (uint32_t)(((halo && tp.mode == 0) ? row_px : 8) * kc * 2) >> 4;
         for (size_t i = 0; i < members.size(); ++i) {
           const Tap& o = p.taps[ph][members[i]];
-          const uint32_t row_off = (uint32_t)((o.oy - oy_min) * TW * kc * 2) >> 4;
+          const uint32_t off = (uint32_t)(((o.oy - oy_min) * row_px + (o.ox - ox_min)) * kc * 2) >> 4;
           const uint32_t wblk = (uint32_t)(o.wkb0 - p.wkb_phase0[ph] + ch);
-          st.tap[i] = row_off | (wblk << 16);
+          st.tap[i] = off | (wblk << 16);
         }
       }
     }
@@ -931,7 +975,7 @@ Plan build_plan(const disco_conv_desc* d) {
   const int fixed = b_bytes + 256 + epi_bytes + 1024;
   int stages = (225 * 1024 - fixed) / a_stage;
   if (stages > 8) stages = 8;
-  if (stages < 3) return p;
+  if (stages < 2) return p;
   p.resident = true;
   p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_bytes;
   p.res_smem_bytes = stages * a_stage + fixed;
@@ -966,14 +1010,13 @@ int encode(disco_handle* h, CUtensorMap* tm, void* base, int rank, const cuuint6
   return DISCO_OK;
 }
 
-int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
-int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 struct Cached {
   TcParams params;
   Plan plan;
   int grid;
+  void* tables_dev = nullptr;
 };
 std::mutex g_mu;
 std::map<std::string, Cached> g_cache;
@@ -1085,12 +1128,18 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   if (!env_read) {
     const char* e = getenv("DISCO_TC_RESIDENT");
     if (e && e[0] == '0') g_allow_resident = false;
+    const char* hm = getenv("DISCO_TC_HALO");
+    if (hm) g_halo_mode = atoi(hm);
     env_read = true;
   }
   std::string key(reinterpret_cast<const char*>(d), sizeof(*d));
   key.append(reinterpret_cast<const char*>(&h->device), sizeof(int));
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_cache.size() > 8192) g_cache.clear();
+  if (g_cache.size() > 8192) {
+    cudaStreamSynchronize(st);
+    for (auto& kv : g_cache) cudaFree(kv.second.tables_dev);
+    g_cache.clear();
+  }
   auto it = g_cache.find(key);
   if (it == g_cache.end()) {
     Cached c;
@@ -1115,16 +1164,25 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     P.n_phase = pl.n_phase; P.os = pl.os;
     P.B = d->batch; P.Hg = pl.Hg; P.Wg = pl.Wg;
     const int TW = pl.TW, TH = pl.TH, NB = pl.NB;
-    memcpy(P.steps, pl.steps, sizeof(P.steps));
+    {
+      std::vector<uint8_t> host(sizeof(pl.steps) + sizeof(pl.taps));
+      memcpy(host.data(), pl.steps, sizeof(pl.steps));
+      memcpy(host.data() + sizeof(pl.steps), pl.taps, sizeof(pl.taps));
+      void* dev = nullptr;
+      DISCO_CUDA(cudaMalloc(&dev, host.size()));
+      DISCO_CUDA(cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice));
+      P.tables = reinterpret_cast<const uint32_t*>(dev);
+      c.tables_dev = dev;
+    }
     memcpy(P.nsteps, pl.nsteps, sizeof(P.nsteps));
     memcpy(P.wkb_phase0, pl.wkb_phase0, sizeof(P.wkb_phase0));
     P.res_stages = pl.res_stages; P.res_a_stage_bytes = pl.res_a_stage_bytes; P.res_b_bytes = pl.res_b_bytes;
+    P.halo_bo_mask = (pl.halo && g_halo_mode == 2) ? (pl.KC == 64 ? 7 : (pl.KC == 32 ? 3 : 1)) : 0;
     P.TW = TW; P.TH = TH; P.NB = NB; P.tw_log2 = ilog2(TW); P.th_log2 = ilog2(TH);
     P.tiles_x = (P.Wg + TW - 1) / TW; P.tiles_y = (P.Hg + TH - 1) / TH; P.tiles_b = (P.B + NB - 1) / NB;
     P.tiles_n = pl.cout_pad / pl.BN;
     P.tiles_total = P.tiles_x * P.tiles_y * P.tiles_b * P.tiles_n * pl.n_phase;
     P.cout_pad = pl.cout_pad;
-    memcpy(P.taps, pl.taps, sizeof(P.taps));
     memcpy(P.ntaps, pl.ntaps, sizeof(P.ntaps));
     memcpy(P.kblocks, pl.kblocks, sizeof(P.kblocks));
     P.Ho = d->Ho; P.Wo = d->Wo; P.Cout = d->Cout; P.act = d->act; P.head = d->head; P.slope = d->slope;
@@ -1149,7 +1207,8 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
       if (mode == 0) {
         cuuint64_t dims[4] = {Cc, Wd, Hd, Bd};
         cuuint64_t str[3] = {Cc * 2, Wd * Cc * 2, Hd * Wd * Cc * 2};
-        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)TW, (cuuint32_t)(pl.resident ? TH + pl.span[s] : TH), (cuuint32_t)NB};
+        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)(pl.resident ? TW + pl.spanx[s] : TW),
+                             (cuuint32_t)(pl.resident ? TH + pl.span[s] : TH), (cuuint32_t)NB};
         rc = encode(h, &P.tmA[s], const_cast<void*>(src.ptr), 4, dims, str, box, pl.KC);
       } else {
         DISCO_CHECK_ARG(src.H % 2 == 0 && src.W % 2 == 0, "conv_tc: stride-2 source must have even H, W");
