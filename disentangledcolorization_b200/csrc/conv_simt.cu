@@ -183,17 +183,21 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams P) {
 
 // ------------------------------------------------------------------------------------------------
 // Cin == 1 first layers (repnet.conv1_2.0: 1->64, segnet.conv0a: 1->16): HBM-bound (4 B in, 2*Cout B out
-// per pixel).  One thread = one pixel x 8 output channels; its 72 weights stay in registers across a
-// grid-stride loop; a warp writes 32 x 16 B = 512 contiguous bytes of the NHWC output.
+// per pixel).  One thread = 4 consecutive pixels of a row x 8 output channels: the 3x6 gray window is loaded once
+// and slid across the 4 pixels, the 72 weights stay in registers while the block walks down the rows it owns,
+// and every store instruction of a warp writes whole 128-byte lines of the NHWC output.
+// grid = (ceil(W / pixels_per_block), row blocks), blockDim = 256.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) conv_c1_kernel(const float* __restrict__ gray, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) conv_c1_kernel(const float* __restrict__ gray, const float* __restrict__ w,
                                                       const float* __restrict__ bias, const float* __restrict__ ps,
-                                                      const float* __restrict__ pb, int B, int H, int W, int Cout, int act,
+                                                      const float* __restrict__ pb, int rows, int H, int W, int Cout, int act,
                                                       float slope, T* __restrict__ out) {
-  const int tpp = Cout >> 3;                       // threads per pixel
-  const unsigned total = (unsigned)H * W * tpp;    // work items per image (blockIdx.y = image)
-  const int c0 = (threadIdx.x % tpp) * 8;          // blockDim.x is a multiple of tpp
+  constexpr int PX = 4;
+  const int tpp = Cout >> 3;                          // threads per pixel group
+  const int cgi = threadIdx.x % tpp, pg = threadIdx.x / tpp;
+  const int c0 = cgi * 8;
+  const int x0 = (blockIdx.x * (256 / tpp) + pg) * PX;
   float wr[9][8], br[8], sr[8], hr[8];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -205,37 +209,49 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const float* __restrict__ 
     sr[j] = ps ? ps[c0 + j] : 1.f;
     hr[j] = pb ? pb[c0 + j] : 0.f;
   }
-  const size_t n = blockIdx.y;
-  const float* g = gray + n * H * W;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned pix_in = i / tpp;
-    const int x = (int)(pix_in % (unsigned)W), y = (int)(pix_in / (unsigned)W);
-    const size_t pix = n * H * W + pix_in;
-    float v[8];
+  if (x0 >= W) return;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {     // r = n * H + y
+    const int y = r % H;
+    const float* g = gray + (size_t)(r - y) * W;           // image base
+    float win[3][PX + 2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = br[j];
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      const bool yok = yy >= 0 && yy < H;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      const float gv = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(g + yy * W + xx) : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(gv, wr[t][j], v[j]);
+      for (int dx = 0; dx < PX + 2; ++dx) {
+        const int xx = x0 + dx - 1;
+        win[dy][dx] = (yok && xx >= 0 && xx < W) ? __ldg(g + (size_t)yy * W + xx) : 0.f;
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, slope) * sr[j] + hr[j];
-    T* o = out + pix * Cout + c0;
-    if (sizeof(T) == 2) {
-      uint32_t pk[4];
+    for (int p = 0; p < PX; ++p) {
+      if (x0 + p >= W) break;
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int j = 0; j < 8; ++j) v[j] = br[j];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float gv = win[t / 3][p + t % 3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(gv, wr[t][j], v[j]);
       }
-      *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    } else {
-      float* of = reinterpret_cast<float*>(o);
-      *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act, slope) * sr[j] + hr[j];
+      T* o = out + ((size_t)r * W + x0 + p) * Cout + c0;
+      if (sizeof(T) == 2) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+        float* of = reinterpret_cast<float*>(o);
+        *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
   }
 }
@@ -250,13 +266,14 @@ int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st)
   if (d->dtype == DISCO_BF16 && d->kind == DISCO_CONV3 && d->n_src == 1 && d->src[0].C == 1 && d->src[0].is_f32 &&
       d->stride == 1 && !d->src[0].up2 && d->head == DISCO_HEAD_NONE && !d->residual && d->Cout % 8 == 0 &&
       256 % (d->Cout / 8) == 0 && d->batch <= 65535 && (long long)d->Ho * d->Wo * (d->Cout / 8) < (1ll << 31)) {
-    const long long items = (long long)d->Ho * d->Wo * (d->Cout / 8);     // per image
-    long long bx = (items + 255) / 256;
-    const long long cap = ((long long)h->sm_count * 16 + d->batch - 1) / d->batch;
-    if (bx > cap) bx = cap < 1 ? 1 : cap;
-    conv_c1_kernel<__nv_bfloat16><<<dim3((unsigned)bx, d->batch), 256, 0, st>>>(
+    const int tpp = d->Cout / 8, px_per_block = (256 / tpp) * 4;
+    const int rows = d->batch * d->Ho;
+    const int gx = (d->Wo + px_per_block - 1) / px_per_block;
+    int gy = (h->sm_count * 8 + gx - 1) / gx;
+    if (gy > rows) gy = rows;
+    conv_c1_kernel<__nv_bfloat16><<<dim3(gx, gy), 256, 0, st>>>(
         reinterpret_cast<const float*>(d->src[0].ptr), reinterpret_cast<const float*>(d->weights) + d->src[0].w_off, d->bias,
-        d->post_scale, d->post_shift, d->batch, d->Ho, d->Wo, d->Cout, d->act, d->slope,
+        d->post_scale, d->post_shift, rows, d->Ho, d->Wo, d->Cout, d->act, d->slope,
         reinterpret_cast<__nv_bfloat16*>(d->out));
     DISCO_LAUNCH_CHECK(h);
     return DISCO_OK;

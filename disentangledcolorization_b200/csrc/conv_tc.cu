@@ -248,7 +248,10 @@ template <int BN, int KC>
 struct Cfg {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // K-blocks per pipeline stage: narrow tiles (N <= 128) finish a K-block's MMAs in <= 256 cycles, which does not
+  // cover an mbarrier round trip, so two K-blocks share one stage / one full-empty handshake
+  static constexpr int KB = BN <= 128 ? 2 : 1;
+  static constexpr int STAGE_BYTES = KB * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -494,8 +497,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   using C = Cfg<BN, KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smem_a = smem;                                        // [stage][KB] A tiles
+  uint8_t* smem_b = smem + C::STAGES * C::KB * C::A_BYTES;       // [stage][KB] B tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
@@ -538,19 +541,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int phase = it.phase, nt = it.nt;
         const int x0 = it.xt * P.TW, y0 = it.yt * P.TH, b0 = it.bt * P.NB;
         const int ntap = P.ntaps[phase];
+        int sub = 0;                        // K-blocks already issued into the current stage
+        int left = P.kblocks[phase];        // K-blocks of this tile not yet issued
         for (int t = 0; t < ntap; ++t) {
           const Tap tp = s_taps[phase * kMaxTaps + t];
           for (int ch = 0; ch < tp.nchunks; ++ch) {
-            mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
-            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-            void* da = smem_a + stage * C::A_BYTES;
-            void* db = smem_b + stage * C::B_BYTES;
+            if (sub == 0) {
+              mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
+              const int n = left < C::KB ? left : C::KB;
+              mbar_expect_tx(&full[stage], (uint32_t)(n * (C::A_BYTES + C::B_BYTES)));
+            }
+            void* da = smem_a + (stage * C::KB + sub) * C::A_BYTES;
+            void* db = smem_b + (stage * C::KB + sub) * C::B_BYTES;
             if (tp.mode == 0)
               tma_load_4d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, y0 + tp.oy, b0);
             else
               tma_load_5d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, tp.py, y0 + tp.oy, b0);
             tma_load_2d(db, &P.tmB, &full[stage], 0, (tp.wkb0 + ch) * P.cout_pad + nt * BN);
-            if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+            --left;
+            if (++sub == C::KB || left == 0) {
+              sub = 0;
+              if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+            }
           }
         }
       }
@@ -573,13 +585,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(&tempty[as], aph ^ 1, perr);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb; kb += C::KB) {
           mbar_wait(&full[stage], ph, perr);
           tc_fence_after();
-          const uint64_t ad = desc0 + (uint64_t)((a_base16 + stage * (C::A_BYTES >> 4)) & 0x3fffu);
-          const uint64_t bd = desc0 + (uint64_t)((b_base16 + stage * (C::B_BYTES >> 4)) & 0x3fffu);
 #pragma unroll
-          for (int k = 0; k < NK; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          for (int sb = 0; sb < C::KB; ++sb) {
+            if (kb + sb < nkb) {
+              const uint64_t ad = desc0 + (uint64_t)((a_base16 + (stage * C::KB + sb) * (C::A_BYTES >> 4)) & 0x3fffu);
+              const uint64_t bd = desc0 + (uint64_t)((b_base16 + (stage * C::KB + sb) * (C::B_BYTES >> 4)) & 0x3fffu);
+#pragma unroll
+              for (int k = 0; k < NK; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+            }
+          }
           umma_commit(&empty[stage]);
           if (++stage == (uint32_t)C::STAGES) { stage = 0; ph ^= 1; }
         }
@@ -904,7 +921,31 @@ Plan build_plan(const disco_conv_desc* d) {
   // halo mode: 8-pixel-wide tiles so that an 8-row MMA group is 8 consecutive pixels of one image row; ONE box
   // with the full (TW+2) x (TH+2) halo then serves all taps of a source (A descriptors start at arbitrary pixel
   // offsets inside the box; the swizzle phase is carried by the address / descriptor base offset)
-  const bool halo = g_halo_mode != 0 && p.Wg % 8 == 0 && pow2_ceil_(p.Hg) >= 16;
+  bool halo = g_halo_mode != 0 && p.Wg % 8 == 0 && pow2_ceil_(p.Hg) >= 16;
+  if (halo) {
+    // steps per tile with column grouping vs. with halo boxes (worst phase); halo tiles are 8 pixels wide, which makes
+    // the stride-2-sampled taps of skip sources (one step each in both schemes) slightly costlier, so require a real gain
+    int worst_grouped = 0, worst_halo = 0;
+    for (int ph = 0; ph < p.n_phase; ++ph) {
+      int grouped = 0, with_halo = 0;
+      for (int s = 0; s < d->n_src; ++s) {
+        bool seen_ox[8] = {false};
+        int n0 = 0, n1 = 0, nch = 0;
+        for (int t = 0; t < p.ntaps[ph]; ++t) {
+          const Tap& tp = p.taps[ph][t];
+          if (tp.src != s) continue;
+          nch = tp.nchunks;
+          if (tp.mode == 0) { if (!seen_ox[tp.ox + 4]) { seen_ox[tp.ox + 4] = true; n0++; } }
+          else n1++;
+        }
+        grouped += (n0 + n1) * nch;
+        with_halo += ((n0 ? 1 : 0) + n1) * nch;
+      }
+      worst_grouped = grouped > worst_grouped ? grouped : worst_grouped;
+      worst_halo = with_halo > worst_halo ? with_halo : worst_halo;
+    }
+    halo = worst_halo * 2 <= worst_grouped;
+  }
   if (halo) { TW = 8; TH = 16; p.TW = TW; p.TH = TH; p.NB = 1; }
   p.halo = halo;
   // per-source extents of the mode-0 tap offsets (box = tile + span)

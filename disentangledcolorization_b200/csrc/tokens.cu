@@ -109,18 +109,38 @@ __global__ void __launch_bounds__(256) linear_kernel(const disco_linear_desc d) 
 }
 
 // ------------------------------------------------------------------------------------------
-// attention core: grid (B*8, ceil(S/128)), 128 threads, thread = query; K/V of the head in smem
+// attention core: grid (B*8, ceil(S/128)), 128 threads, thread = query; K/V of the head in smem.
+// One pass over the keys with a running maximum (online softmax, fp32), four keys per iteration for ILP.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot8(const float (&q)[8], const float* k) {
+  const float4 a = *reinterpret_cast<const float4*>(k);
+  const float4 b = *reinterpret_cast<const float4*>(k + 4);
+  float s = q[0] * a.x;
+  s = fmaf(q[1], a.y, s); s = fmaf(q[2], a.z, s); s = fmaf(q[3], a.w, s);
+  s = fmaf(q[4], b.x, s); s = fmaf(q[5], b.y, s); s = fmaf(q[6], b.z, s); s = fmaf(q[7], b.w, s);
+  return s;
+}
+__device__ __forceinline__ void axpy8(float (&o)[8], float p, const float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(v);
+  const float4 b = *reinterpret_cast<const float4*>(v + 4);
+  o[0] = fmaf(p, a.x, o[0]); o[1] = fmaf(p, a.y, o[1]); o[2] = fmaf(p, a.z, o[2]); o[3] = fmaf(p, a.w, o[3]);
+  o[4] = fmaf(p, b.x, o[4]); o[5] = fmaf(p, b.y, o[5]); o[6] = fmaf(p, b.z, o[6]); o[7] = fmaf(p, b.w, o[7]);
+}
+
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ out) {
-  extern __shared__ float kv[];   // K [S][8] then V [S][8]
+  extern __shared__ float kv[];   // K [S4][8] then V [S4][8], S4 = S rounded up to 4 (padding rows are zero)
+  const int S4 = (S + 3) & ~3;
   float* Ks = kv;
-  float* Vs = kv + (size_t)S * 8;
+  float* Vs = kv + (size_t)S4 * 8;
   const int n = blockIdx.x >> 3, hd = blockIdx.x & 7;
   const float* base = qkv + (size_t)n * S * 192;
-  for (int e = threadIdx.x; e < S * 2; e += 128) {
+  for (int e = threadIdx.x; e < S4 * 2; e += 128) {
     const int t = e >> 1, half = e & 1;
-    const float4 k4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 64 + hd * 8 + half * 4);
-    const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 128 + hd * 8 + half * 4);
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+    if (t < S) {
+      k4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 64 + hd * 8 + half * 4);
+      v4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 128 + hd * 8 + half * 4);
+    }
     *reinterpret_cast<float4*>(Ks + t * 8 + half * 4) = k4;
     *reinterpret_cast<float4*>(Vs + t * 8 + half * 4) = v4;
   }
@@ -133,28 +153,22 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     const float4 b = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8 + 4);
     q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
   }
-  float mx = -FLT_MAX;
-  for (int j = 0; j < S; ++j) {
-    const float4 a = *reinterpret_cast<const float4*>(Ks + j * 8);
-    const float4 b = *reinterpret_cast<const float4*>(Ks + j * 8 + 4);
-    float s = q[0] * a.x;
-    s = fmaf(q[1], a.y, s); s = fmaf(q[2], a.z, s); s = fmaf(q[3], a.w, s);
-    s = fmaf(q[4], b.x, s); s = fmaf(q[5], b.y, s); s = fmaf(q[6], b.z, s); s = fmaf(q[7], b.w, s);
-    mx = fmaxf(mx, s);
-  }
-  float sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j = 0; j < S; ++j) {
-    const float4 a = *reinterpret_cast<const float4*>(Ks + j * 8);
-    const float4 b = *reinterpret_cast<const float4*>(Ks + j * 8 + 4);
-    float s = q[0] * a.x;
-    s = fmaf(q[1], a.y, s); s = fmaf(q[2], a.z, s); s = fmaf(q[3], a.w, s);
-    s = fmaf(q[4], b.x, s); s = fmaf(q[5], b.y, s); s = fmaf(q[6], b.z, s); s = fmaf(q[7], b.w, s);
-    const float e = expf(s - mx);
-    sum += e;
-    const float4 va = *reinterpret_cast<const float4*>(Vs + j * 8);
-    const float4 vb = *reinterpret_cast<const float4*>(Vs + j * 8 + 4);
-    o[0] = fmaf(e, va.x, o[0]); o[1] = fmaf(e, va.y, o[1]); o[2] = fmaf(e, va.z, o[2]); o[3] = fmaf(e, va.w, o[3]);
-    o[4] = fmaf(e, vb.x, o[4]); o[5] = fmaf(e, vb.y, o[5]); o[6] = fmaf(e, vb.z, o[6]); o[7] = fmaf(e, vb.w, o[7]);
+  float mx = -FLT_MAX, sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < S4; j += 4) {
+    float s0 = dot8(q, Ks + j * 8), s1 = dot8(q, Ks + j * 8 + 8), s2 = dot8(q, Ks + j * 8 + 16), s3 = dot8(q, Ks + j * 8 + 24);
+    if (j + 3 >= S) {                      // tail: padded keys must not contribute
+      if (j + 1 >= S) s1 = -FLT_MAX;
+      if (j + 2 >= S) s2 = -FLT_MAX;
+      s3 = -FLT_MAX;
+    }
+    const float mnew = fmaxf(fmaxf(mx, fmaxf(s0, s1)), fmaxf(s2, s3));
+    const float corr = expf(mx - mnew);
+    const float p0 = expf(s0 - mnew), p1 = expf(s1 - mnew), p2 = expf(s2 - mnew), p3 = expf(s3 - mnew);
+    sum = fmaf(sum, corr, (p0 + p1) + (p2 + p3));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] *= corr;
+    axpy8(o, p0, Vs + j * 8); axpy8(o, p1, Vs + j * 8 + 8); axpy8(o, p2, Vs + j * 8 + 16); axpy8(o, p3, Vs + j * 8 + 24);
+    mx = mnew;
   }
   const float inv = 1.0f / sum;
   float* dst = out + ((size_t)n * S + qi) * 64 + hd * 8;
@@ -375,7 +389,7 @@ extern "C" int disco_linear(disco_handle* h, const disco_linear_desc* d, void* s
 
 extern "C" int disco_attention(disco_handle* h, const float* qkv, int batch, int S, float* out, void* stream) {
   DISCO_CHECK_ARG(h && qkv && out && batch > 0 && S > 0, "attention: bad argument");
-  const size_t smem = (size_t)S * 16 * sizeof(float);
+  const size_t smem = (size_t)((S + 3) & ~3) * 16 * sizeof(float);
   DISCO_CHECK_ARG(smem <= 200 * 1024, "attention: S=%d too large for the shared-memory K/V stage", S);
   if (smem > 48 * 1024)
     DISCO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
