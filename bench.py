@@ -32,6 +32,9 @@ H = W = 256
 K_CLUSTERS = 8
 FLOP_PER_IMAGE = 255.47e9        # SURVEY.md section 8d / BASELINE.md section 3
 METRIC = "256x256 images/sec"
+# --workload c4: BASELINE config 4 (batch 32, 512x512 --no_resize path, n_clusters=16); not the headline metric
+WORKLOADS = {"c2": dict(batch=64, hw=256, k=8, flop=255.47e9, metric="256x256 images/sec"),
+             "c4": dict(batch=32, hw=512, k=16, flop=1024.3e9, metric="512x512 images/sec")}
 
 
 def _peaks():
@@ -134,7 +137,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batch={BATCH_PER_GPU} 256x256 forward, n_clusters=8 (bounded sample: {sample} images/step)"},
+        "config": {"workload": f"batch={BATCH_PER_GPU} {H}x{W} forward, n_clusters={K_CLUSTERS} (bounded sample: {sample} images/step)"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -243,7 +246,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"batch={B}/GPU 256x256 {args.precision} forward, n_clusters=8, 1xB200 per rank"
+            "config": {"workload": f"batch={B}/GPU {H}x{W} {args.precision} forward, n_clusters={K_CLUSTERS}, 1xB200 per rank"
                                    + (", one NCCL all-gather of pred_colors" if world > 1 else ""),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: each step streams ~10 GB of activations, far larger than the 126 MB L2"},
@@ -260,7 +263,7 @@ def run_ours(args):
                          "whole_step_frac": (B * FLOP_PER_IMAGE / (ms / args.steps / 1e3) / 1e12) / peak,
                          "top": prof["top"]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"8 images 256x256, oracle port of the reference forward, fp32 torch CPU, {cpu_s:.1f} s"},
+                             "sample": f"8 images {H}x{W}, oracle port of the reference forward, fp32 torch CPU, {cpu_s:.1f} s"},
         }
     if world > 1:
         dist.barrier()
@@ -276,9 +279,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS), help="c2 = headline (batch 64, 256x256, K=8)")
     ap.add_argument("--dump-profile", default=None, help="write the per-op conv timing table (JSON) to this path")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle timing (profiling runs)")
     args = ap.parse_args()
+    global BATCH_PER_GPU, H, W, K_CLUSTERS, FLOP_PER_IMAGE, METRIC
+    wl = WORKLOADS[args.workload]
+    BATCH_PER_GPU, H, W, K_CLUSTERS, FLOP_PER_IMAGE, METRIC = wl["batch"], wl["hw"], wl["hw"], wl["k"], wl["flop"], wl["metric"]
     if args.impl == "reference":
         run_reference(args)
     else:

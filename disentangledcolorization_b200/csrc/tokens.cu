@@ -373,6 +373,59 @@ __global__ void token_labels_kernel(int mode, const float* __restrict__ src, con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// diverse anchor colours (sampled_T > 0): per token the 10 most probable bins (stable order: ties keep the lower
+// bin index, like torch.sort on CPU), then T=0 top-1, T=1 the candidate farthest from top-1, T=2 the candidate
+// maximising d(.,top-1) + d(.,T=1 pick)  (reference models/anchor_gen.py:54-90).  One thread per token.
+// ------------------------------------------------------------------------------------------
+__global__ void token_sample3_kernel(const float* __restrict__ logits, const float* __restrict__ table, int B, int S,
+                                     int32_t* __restrict__ labels3, float* __restrict__ colors3) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S) return;
+  const int n = idx / S, t = idx % S;
+  float tv[10];
+  int ti[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { tv[i] = -FLT_MAX; ti[i] = 0; }
+  const float* col = logits + (size_t)n * 313 * S + t;
+  for (int c = 0; c < 313; ++c) {
+    const float v = col[(size_t)c * S];
+    if (v > tv[9]) {
+      float cv = v; int ci = c;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        if (cv > tv[i]) { const float fv = tv[i]; const int fi = ti[i]; tv[i] = cv; ti[i] = ci; cv = fv; ci = fi; }
+      }
+    }
+  }
+  float ca[10], cb[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { ca[i] = table[ti[i] * 2] / 110.0f; cb[i] = table[ti[i] * 2 + 1] / 110.0f; }
+  float d0[10];
+  int p1 = 0; float best = -1.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float da = ca[i] - ca[0], db = cb[i] - cb[0];
+    d0[i] = sqrtf(da * da + db * db);
+    if (d0[i] > best) { best = d0[i]; p1 = i; }
+  }
+  int p2 = 0; best = -1.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float da = ca[i] - ca[p1], db = cb[i] - cb[p1];
+    const float sc = d0[i] + sqrtf(da * da + db * db);
+    if (sc > best) { best = sc; p2 = i; }
+  }
+  const int pick[3] = {0, p1, p2};
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const int k = pick[v];
+    labels3[(size_t)v * B * S + idx] = ti[k];
+    colors3[(((size_t)v * B + n) * 2 + 0) * S + t] = ca[k];
+    colors3[(((size_t)v * B + n) * 2 + 1) * S + t] = cb[k];
+  }
+}
+
 }  // namespace
 
 extern "C" int disco_linear(disco_handle* h, const disco_linear_desc* d, void* stream) {
@@ -415,6 +468,14 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   kmeans_anchor_kernel<<<batch, 256, use_smem ? dyn : 0, st>>>(a, 0, use_smem);
   DISCO_LAUNCH_CHECK(h);
   kmeans_anchor_kernel<<<1, 256, use_smem ? dyn : 0, st>>>(a, 1, use_smem);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}
+
+extern "C" int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
+                                   int32_t* labels3, float* colors3, void* stream) {
+  DISCO_CHECK_ARG(h && logits && q_to_ab && labels3 && colors3, "token_sample3: null pointer");
+  token_sample3_kernel<<<(batch * S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, q_to_ab, batch, S, labels3, colors3);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }

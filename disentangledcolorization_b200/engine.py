@@ -69,7 +69,7 @@ class _PackedConv:
 
 
 class Engine:
-    def __init__(self, state_dict, device, precision="bf16", n_clusters=8, sp_size=16, enhanced=True):
+    def __init__(self, state_dict, device, precision="bf16", n_clusters=8, sp_size=16, enhanced=True, random_hint=False):
         if precision not in _DT:
             raise ValueError(f"precision must be one of {list(_DT)}")
         if sp_size != 16:
@@ -85,6 +85,7 @@ class Engine:
         self.dt_code, self.dt_torch = _DT[precision]
         self.n_clusters = n_clusters
         self.enhanced = enhanced
+        self.random_hint = random_hint
         self._ws = {}
         self._pos = {}
         self._pending_rng = None
@@ -288,11 +289,12 @@ class Engine:
         self._resolve_rng()
         if gray.dim() != 4 or gray.shape[1] != 1:
             raise _lib.DiscoError(f"input_grays must be (N,1,H,W), got {tuple(gray.shape)}")
-        if sampled_T > 0:
-            raise _lib.DiscoError("sampled_T > 0 (--diverse) is not built yet")
         B, _, H, W = gray.shape
         if B == 0:
             raise _lib.DiscoError("empty batch")
+        if sampled_T > 0 and B != 1:
+            raise _lib.DiscoError("sampled_T > 0 (--diverse) needs a batch of 1, as in the reference "
+                                  "(the expand at models/model.py:155-159 fails otherwise)")
         dev = self.device
         gray = gray.to(device=dev, dtype=torch.float32).contiguous()
         ab = ab.to(device=dev, dtype=torch.float32).contiguous()
@@ -304,6 +306,7 @@ class Engine:
         lib, hd = self.lib, self.handle.h
         M = B * S
 
+        # ---- first half: affinity, features, tokens, colour-probability branch (model.py:104-135)
         self._run_net("segnet", ws, B, gray, stream)                                   # model.py:104
         self._run_net("repnet", ws, B, gray, stream)                                   # model.py:105
         affinity = bufs["affinity"]
@@ -315,7 +318,16 @@ class Engine:
         pal_logit = torch.empty(B, 313, h, w, dtype=torch.float32, device=dev)
         self._linear(stream, tok["enc"], self.mid_w, pal_logit, transpose_S=S)          # model.py:134-135
 
-        if hint_mask is None:                                                           # model.py:140-141
+        # ---- anchors (model.py:140-141)
+        if hint_mask is not None:
+            hint = hint_mask.to(device=dev, dtype=torch.float32).reshape(B, 1, h, w).contiguous()
+        elif self.random_hint:                                                          # anchor_gen.py:102-106
+            import random
+            mask = np.zeros((B, S), np.float32)
+            for n in range(B):                                                          # basic.py:42-47
+                mask[n, random.sample(range(0, S), random.randint(self.n_clusters, self.n_clusters))] = 1
+            hint = torch.from_numpy(mask.reshape(B, 1, h, w)).to(dev)
+        else:
             K = self.n_clusters
             if init_idx is not None:                 # sharded runs: rows drawn for the global batch (dist.py)
                 tok["init_idx_host"].copy_(torch.as_tensor(np.asarray(init_idx, dtype=np.int32)).view(B, K))
@@ -335,32 +347,48 @@ class Engine:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             self._pending_rng = (state, tok["events_host"], ev, S)
+
+        # ---- anchor colours and token labels (model.py:142-168)
+        if sampled_T > 0:                                                               # model.py:148-159, N = 3
+            B2 = 3
+            ws2 = self._workspace(B2, H, W)
+            tok2 = ws2["tok"]
+            spix_colors = torch.empty(3, 2, h, w, dtype=torch.float32, device=dev)
+            _lib.check(lib.disco_token_sample3(hd, _ptr(pal_logit), _ptr(self.q_to_ab), 1, S, _ptr(tok2["labels"]),
+                                               _ptr(spix_colors), stream), "disco_token_sample3")
+            tok2["tokens"].copy_(tok["tokens"].expand(3, -1, -1))
+            hint = hint.expand(3, -1, -1, -1).contiguous()
+            gray2 = gray.expand(3, -1, -1, -1).contiguous()
+            ws2["bufs"]["affinity"].copy_(affinity.expand(3, -1, -1, -1))
         else:
-            hint = hint_mask.to(device=dev, dtype=torch.float32).reshape(B, 1, h, w).contiguous()
+            B2, ws2, tok2, gray2 = B, ws, tok, gray
+            spix_colors = torch.empty(B, 2, h, w, dtype=torch.float32, device=dev)
+            if sampled_T < 0:                                                           # model.py:145-147,166
+                spix_colors.copy_(tok["spix_ab"])
+                _lib.check(lib.disco_token_labels(hd, 1, _ptr(tok["spix_ab"]), _ptr(self.q_to_ab), B, S,
+                                                  _ptr(tok["labels"]), None, stream), "disco_token_labels")
+            else:                                                                       # model.py:161,166
+                _lib.check(lib.disco_token_labels(hd, 0, _ptr(pal_logit), _ptr(self.q_to_ab), B, S,
+                                                  _ptr(tok["labels"]), _ptr(spix_colors), stream), "disco_token_labels")
 
-        spix_colors = torch.empty(B, 2, h, w, dtype=torch.float32, device=dev)
-        if sampled_T < 0:                                                               # model.py:145-147,166
-            spix_colors.copy_(tok["spix_ab"])
-            _lib.check(lib.disco_token_labels(hd, 1, _ptr(tok["spix_ab"]), _ptr(self.q_to_ab), B, S, _ptr(tok["labels"]),
-                                              None, stream), "disco_token_labels")
-        else:                                                                           # model.py:161,166
-            _lib.check(lib.disco_token_labels(hd, 0, _ptr(pal_logit), _ptr(self.q_to_ab), B, S, _ptr(tok["labels"]),
-                                              _ptr(spix_colors), stream), "disco_token_labels")
-        self._linear(stream, tokens, self.emb_src, tok["hint_seq"],
-                     hint=(hint, tok["labels"], self.emb_tab))                          # model.py:175-185
-        self._encoder_stack("hintpath", tok["hint_seq"], tok["dec"], ws, B, stream)     # model.py:186
-        ref_logit = torch.empty(B, 313, h, w, dtype=torch.float32, device=dev)
-        self._linear(stream, tok["dec"], self.trg_w, ref_logit, transpose_S=S)          # model.py:187-189
-
+        # ---- second half: hint embedding, hint path, un-pooling, enhancement (model.py:175-197)
+        M2 = B2 * S
+        bufs2 = ws2["bufs"]
+        affinity2 = bufs2["affinity"]
+        self._linear(stream, tok2["tokens"].view(M2, 64), self.emb_src, tok2["hint_seq"],
+                     hint=(hint, tok2["labels"], self.emb_tab))                         # model.py:175-185
+        self._encoder_stack("hintpath", tok2["hint_seq"], tok2["dec"], ws2, B2, stream)  # model.py:186
+        ref_logit = torch.empty(B2, 313, h, w, dtype=torch.float32, device=dev)
+        self._linear(stream, tok2["dec"], self.trg_w, ref_logit, transpose_S=S)         # model.py:187-189
         pred = None
         if self.enhanced:
-            _lib.check(lib.disco_upfeat(hd, self.dt_code, _ptr(tok["dec"]), _ptr(affinity), B, H, W, 64,
-                                        _ptr(bufs["full_feats"]), stream), "disco_upfeat")   # model.py:194-195
-            self._run_net("enhanceNet", ws, B, gray, stream)                            # model.py:196-197
-            pred = bufs["pred_colors"].clone()
+            _lib.check(lib.disco_upfeat(hd, self.dt_code, _ptr(tok2["dec"]), _ptr(affinity2), B2, H, W, 64,
+                                        _ptr(bufs2["full_feats"]), stream), "disco_upfeat")   # model.py:194-195
+            self._run_net("enhanceNet", ws2, B2, gray2, stream)                         # model.py:196-197
+            pred = bufs2["pred_colors"].clone()
         if sync_rng:
             self._resolve_rng()
-        return pal_logit, ref_logit, pred, affinity.clone(), spix_colors, hint
+        return pal_logit, ref_logit, pred, affinity2.clone(), spix_colors, hint
 
     @staticmethod
     def algorithmic_flops(op, B, Ho, Wo):

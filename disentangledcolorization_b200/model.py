@@ -47,8 +47,8 @@ class AnchorColorProb(nn.Module):
             unsupported.append("inChannel/outChannel/d_model other than 1/313/64")
         if not use_dense_pos:
             unsupported.append("use_dense_pos=False (the inference CLI forces True, inference.py:165)")
-        if spix_pos or hint2regress or use_mask or random_hint:
-            unsupported.append("spix_pos / hint2regress / use_mask / random_hint")
+        if spix_pos or hint2regress or use_mask:
+            unsupported.append("spix_pos / hint2regress / use_mask")
         if unsupported:
             raise _lib.DiscoError("AnchorColorProb configuration not built: " + "; ".join(unsupported))
         self.sp_size = sp_size
@@ -58,6 +58,7 @@ class AnchorColorProb(nn.Module):
         self.enhanced = enhanced
         self.n_vocab = 313
         self.hint_num = n_clusters
+        self.random_hint = random_hint
         if precision is not None:
             self.precision = precision
         self.segnet = SpixelSeg(inChannel=1, outChannel=9, batchNorm=True)
@@ -111,10 +112,10 @@ class AnchorColorProb(nn.Module):
         from .engine import Engine
         if device is None:
             device = next(self.parameters()).device
-        key = (str(device), self.precision, self.hint_num)
+        key = (str(device), self.precision, self.hint_num, self.random_hint)
         if self._engine is None or self._engine_key != key:
             self._engine = Engine(self.state_dict(), device, precision=self.precision, n_clusters=self.hint_num,
-                                  sp_size=self.sp_size, enhanced=self.enhanced)
+                                  sp_size=self.sp_size, enhanced=self.enhanced, random_hint=self.random_hint)
             self._engine_key = key
         return self._engine
 

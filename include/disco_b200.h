@@ -182,6 +182,13 @@ int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_t* init_idx
 int disco_token_labels(disco_handle* h, int mode, const float* src, const float* q_to_ab, int batch, int S,
                        int32_t* labels, float* colors, void* stream);
 
+/* Diverse anchor colours (sampled_T > 0, the CLI's --diverse): for every token the T=0, T=1 and T=2 picks of
+ * AnchorAnalysis._sample_anchor_colors (models/anchor_gen.py:54-90) among the 10 most probable bins.
+ *   logits fp32 [B,313,S];  labels3 int32 [3][B*S] (picked bin = encode_ab2ind(...).max of the pick);
+ *   colors3 fp32 [3][B,2,S] = q_to_ab[pick]/110 */
+int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
+                        int32_t* labels3, float* colors3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,7 +33,7 @@ def _model(sd, K, precision):
     return m.cuda().eval()
 
 
-CASES = [c for c in golden_cases() if c["T"] <= 0]
+CASES = [c for c in golden_cases() if c["T"] <= 0]   # T=2 (--diverse) has its own test below
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
@@ -96,6 +96,70 @@ def test_forward_bf16_within_stated_tolerance(case, synth_sd):
     own = m(gray.cuda(), ab.cuda(), True, case["T"])
     agree = float((own[5].cpu().numpy() == g["hint_mask"]).mean())
     print(f"{case['name']}: bf16 anchor-site agreement {agree:.3f}")
+
+
+def test_forward_diverse_T2_matches_reference_fixture(synth_sd):
+    """--diverse: sampled_T=2 expands one image into the T=0/1/2 anchor-colour variants (model.py:148-159)."""
+    case = [c for c in golden_cases() if c["name"] == "diverse_64_T2"][0]
+    g = load_golden(case["name"])
+    gray, ab = (torch.from_numpy(t) for t in case_inputs(case))
+    m = _model(synth_sd, case["K"], "fp32")
+    np.random.seed(case["seed"])
+    torch.manual_seed(case["seed"])
+    pal, ref, pred, aff, spix, hint = m(gray.cuda(), ab.cuda(), True, 2)
+    assert tuple(pred.shape) == (3, 2, 64, 64) and tuple(ref.shape) == (3, 313, 4, 4) and tuple(aff.shape) == (3, 9, 64, 64)
+    assert np.array_equal(hint.cpu().numpy(), g["hint_mask"])
+    assert np.abs(spix.cpu().numpy() - g["spix_colors"]).max() < 1e-6, "diverse anchor colours differ"
+    assert np.abs(ref.cpu().numpy() - g["ref_logit"]).max() < 1e-2
+    assert np.abs(pred.cpu().numpy() - g["pred_colors"]).max() < FP32_AB_TOL
+    with pytest.raises(Exception):
+        m(torch.zeros(2, 1, 64, 64).cuda(), torch.zeros(2, 2, 64, 64).cuda(), True, 2)   # N must be 1, as in the reference
+
+
+def test_random_hint_mode_matches_oracle(synth_sd):
+    """--random_hint: anchors from python's random.sample (basic.py:42-47) instead of k-means."""
+    import random
+    import disco_oracle as O
+    from disentangledcolorization_b200 import model, synth
+    gray = torch.from_numpy(synth.make_gray(2, 64, 96, seed=21))
+    ab = torch.zeros(2, 2, 64, 96)
+    m = model.AnchorColorProb(n_clusters=5, enhanced=True, random_hint=True, precision="fp32")
+    m.load_state_dict(synth_sd, strict=True)
+    m = m.cuda().eval()
+    random.seed(3)
+    got = m(gray.cuda(), ab.cuda(), True, 0)
+    random.seed(3)
+    mask = np.zeros((2, 24), np.float32)
+    for n in range(2):
+        mask[n, random.sample(range(0, 24), random.randint(5, 5))] = 1
+    with torch.no_grad():
+        want = O.forward(synth_sd, gray, ab, 5, 0, hint_mask=torch.from_numpy(mask.reshape(2, 1, 4, 6)))
+    assert np.array_equal(got[5].cpu().numpy(), mask.reshape(2, 1, 4, 6)) and float(got[5].sum()) == 10
+    assert (got[2].cpu() - want[2]).abs().max() < FP32_AB_TOL
+
+
+def test_config4_512_no_resize_k16(synth_sd):
+    """BASELINE config 4 shape (512x512, n_clusters=16, S=1024 tokens) at batch 1: fp32 parity with the oracle and a
+    bf16 run (exercises the S=1024 attention / global-memory k-means paths and 32x32 token grids)."""
+    import disco_oracle as O
+    from disentangledcolorization_b200 import synth
+    gray = torch.from_numpy(synth.make_gray(1, 512, 512, seed=33))
+    ab = torch.zeros(1, 2, 512, 512)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    with torch.no_grad():
+        want = O.forward(synth_sd, gray, ab, 16, 0)
+    m = _model(synth_sd, 16, "fp32")
+    np.random.seed(9)
+    torch.manual_seed(9)
+    got = m(gray.cuda(), ab.cuda(), True, 0)
+    assert torch.equal(got[5].cpu(), want[5])
+    assert (got[2].cpu() - want[2]).abs().max() < FP32_AB_TOL
+    mb = _model(synth_sd, 16, "bf16")
+    outb = mb(gray.cuda(), ab.cuda(), True, 0, hint_mask=want[5].cuda())
+    diff = (outb[2].cpu() - want[2]).abs()
+    print(f"512x512 bf16: max|d ab|={float(diff.max()):.4f} mean={float(diff.mean()):.5f}")
+    assert float(diff.max()) < BF16_AB_MAX and float(diff.mean()) < BF16_AB_MEAN
 
 
 def test_error_behaviour(synth_sd):
