@@ -244,19 +244,22 @@ __host__ __device__ constexpr uint32_t instr_desc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int MT = 1>
 struct Cfg {
-  static constexpr int A_BYTES = 128 * KC * 2;
+  // MT = 128-pixel sub-tiles per CTA tile.  MT = 2 (narrow N <= 128 tiles only): one TMA box brings 256 pixels and
+  // both halves are multiplied against the SAME weight tile, which halves the weight traffic per MAC -- N = 128
+  // tiles at 125 B/clk/SM of operand fill are otherwise bound by the L2->SM fabric (~107 B/clk/SM measured).
+  static constexpr int A_BYTES = 128 * MT * KC * 2;
   static constexpr int B_BYTES = BN * KC * 2;
-  // K-blocks per pipeline stage: narrow tiles (N <= 128) finish a K-block's MMAs in <= 256 cycles, which does not
+  // K-blocks per pipeline stage: with MT = 1 narrow tiles finish a K-block's MMAs in <= 256 cycles, which does not
   // cover an mbarrier round trip, so two K-blocks share one stage / one full-empty handshake
-  static constexpr int KB = BN <= 128 ? 2 : 1;
+  static constexpr int KB = (BN <= 128 && MT == 1) ? 2 : 1;
   static constexpr int STAGE_BYTES = KB * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
   // per-epilogue-warp parameter cache: bias | post_scale | post_shift (+ 9 x fp32 L-channel weights when BN <= 64)
-  static constexpr int EPI_COLS = BN >= 32 ? BN / 2 : BN;
+  static constexpr int EPI_COLS = (BN >= 32 && MT == 1) ? BN / 2 : BN;
   static constexpr int EPI_FLOATS = 3 * EPI_COLS + (BN <= 64 ? 9 * EPI_COLS : 0);
   static constexpr int EPI_BYTES = 8 * EPI_FLOATS * 4 + 8 * 2048;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
@@ -294,22 +297,24 @@ struct TileIter {
 // Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
 // lane quarter (w & 3) (a hardware restriction) and, when BN >= 32, the column half ((w - 2) >> 2): two warps per
 // SM sub-partition keep the epilogue's issue rate up (one warp alone runs at IPC ~0.2 on dependent fp32 math).
-template <int BN>
+template <int BN, int MT = 1>
 __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                               float* epi_params, int warp, int lane) {
   constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
-  constexpr int NHALF = BN >= 32 ? 2 : 1;       // column halves (one per warp of a lane quarter)
+  // MT == 1: the two warps of a lane quarter split the columns.  MT == 2: they take one 128-pixel sub-tile each.
+  constexpr int NHALF = (BN >= 32 && MT == 1) ? 2 : 1;   // column halves
   constexpr int COLS = BN / NHALF;              // columns this warp owns
   constexpr int EPI_FLOATS = 3 * COLS + (BN <= 64 ? 9 * COLS : 0);   // per-warp cache: bias|scale|shift(|9 gray taps)
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
-  const bool active = half < NHALF;
-  const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
+  const bool active = half < NHALF * MT;
+  const int sub = MT == 2 ? half : 0;           // 128-pixel sub-tile of this warp
+  const int m = sub * 128 + q * 32 + lane;      // pixel within the tile
   const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
   const uint32_t wp = smem_u32(epi_params + (warp - 2) * EPI_FLOATS);   // this warp's private parameter cache
   const uint32_t stg = smem_u32(epi_params + 8 * EPI_FLOATS) + (warp - 2) * EPI_STAGE;   // output staging patch
-  const int col0 = half * COLS;
+  const int col0 = MT == 2 ? 0 : half * COLS;
   // hot parameters hoisted out of the tile loop (the parameter block is several KB: re-reading it through the
   // constant cache inside the loop stalls on misses)
   const int pTW = P.TW, pTH = P.TH, pNB = P.NB, pWg = P.Wg, pHg = P.Hg, pB = P.B, pos = P.os, pHo = P.Ho, pWo = P.Wo;
@@ -362,7 +367,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     mbar_wait(&tfull[as], aph, perr);
     tc_fence_after();
     if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 1);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (MT * BN) + sub * BN;
     if (phead == DISCO_HEAD_NONE) {
       if (active && P.dbg_mode != 1) {
 #pragma unroll 1
@@ -492,9 +497,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   }
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
-  using C = Cfg<BN, KC>;
+  using C = Cfg<BN, KC, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                        // [stage][KB] A tiles
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int nkb = kbs[it.phase];
         mbar_wait(&tempty[as], aph ^ 1, perr);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * (MT * BN);
         for (int kb = 0; kb < nkb; kb += C::KB) {
           mbar_wait(&full[stage], ph, perr);
           tc_fence_after();
@@ -594,7 +599,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const uint64_t ad = desc0 + (uint64_t)((a_base16 + (stage * C::KB + sb) * (C::A_BYTES >> 4)) & 0x3fffu);
               const uint64_t bd = desc0 + (uint64_t)((b_base16 + (stage * C::KB + sb) * (C::B_BYTES >> 4)) & 0x3fffu);
 #pragma unroll
-              for (int k = 0; k < NK; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+                  umma_bf16(d_tmem + mt * BN, ad + mt * (128 * KC * 2 >> 4) + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+              }
             }
           }
           umma_commit(&empty[stage]);
@@ -605,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
-    epilogue_role<BN>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+    epilogue_role<BN, MT>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
@@ -804,6 +813,7 @@ struct Plan {
   int wkb_phase0[4] = {0, 0, 0, 0};
   // tile shape (phase grid): TW*TH*NB == 128
   int Hg = 0, Wg = 0, TW = 0, TH = 0, NB = 0;
+  int MT = 1;                        // 128-pixel sub-tiles per CTA tile (streaming kernel)
   // resident-weight variant
   bool resident = false;
   Step steps[4][kMaxSteps];
@@ -816,6 +826,7 @@ struct Plan {
 
 int pow2_ceil_(int v) { int p = 1; while (p < v) p *= 2; return p; }
 bool g_allow_resident = true;
+bool g_allow_mt2 = true;
 int g_halo_mode = 1;                 // 0 off, 1 halo tiles (descriptor base_offset 0: the hardware swizzle is a function of
                                      // the absolute smem address -- verified on B200), 2 = experiment: base_offset from addr bits (wrong)
 
@@ -917,7 +928,11 @@ Plan build_plan(const disco_conv_desc* d) {
   int max_kb = 0;
   for (int ph = 0; ph < p.n_phase; ++ph) max_kb = p.kblocks[ph] > max_kb ? p.kblocks[ph] : max_kb;
   const int b_bytes = max_kb * p.BN * kc * 2;
-  if (!g_allow_resident || p.cout_pad != p.BN || p.BN > 64 || p.NB != 1 || TW < 8 || b_bytes > 112 * 1024) return p;
+  if (!g_allow_resident || p.cout_pad != p.BN || p.BN > 64 || p.NB != 1 || TW < 8 || b_bytes > 112 * 1024) {
+    // streaming kernel: 256-pixel tiles for narrow N when a tile stays inside one image
+    if (g_allow_mt2 && p.BN <= 128 && p.NB == 1 && TW * TH == 128 && p.Hg >= 2 * TH) { p.MT = 2; p.TH = 2 * TH; }
+    return p;
+  }
   // halo mode: 8-pixel-wide tiles so that an 8-row MMA group is 8 consecutive pixels of one image row; ONE box
   // with the full (TW+2) x (TH+2) halo then serves all taps of a source (A descriptors start at arbitrary pixel
   // offsets inside the box; the swizzle phase is carried by the address / descriptor base offset)
@@ -1064,15 +1079,15 @@ std::map<std::string, Cached> g_cache;
 int32_t* g_error_flag = nullptr;
 long long* g_dbg = nullptr;
 
-template <int BN, int KC>
+template <int BN, int KC, int MT>
 int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
-  using C = Cfg<BN, KC>;
+  using C = Cfg<BN, KC, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
+  conv_tc_kernel<BN, KC, MT><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
   return DISCO_OK;
 }
 
@@ -1099,15 +1114,24 @@ int launch_res_bn(int BN, const TcParams& P, int grid, int smem_bytes, cudaStrea
 }
 
 template <int KC>
-int launch_bn(int BN, const TcParams& P, int grid, cudaStream_t st) {
-  switch (BN) {
-    case 16: return launch_cfg<16, KC>(P, grid, st);
-    case 32: return launch_cfg<32, KC>(P, grid, st);
-    case 64: return launch_cfg<64, KC>(P, grid, st);
-    case 128: return launch_cfg<128, KC>(P, grid, st);
-    case 256: return launch_cfg<256, KC>(P, grid, st);
+int launch_bn(int BN, int MT, const TcParams& P, int grid, cudaStream_t st) {
+  if (MT == 2) {
+    switch (BN) {
+      case 16: return launch_cfg<16, KC, 2>(P, grid, st);
+      case 32: return launch_cfg<32, KC, 2>(P, grid, st);
+      case 64: return launch_cfg<64, KC, 2>(P, grid, st);
+      case 128: return launch_cfg<128, KC, 2>(P, grid, st);
+    }
+  } else {
+    switch (BN) {
+      case 16: return launch_cfg<16, KC, 1>(P, grid, st);
+      case 32: return launch_cfg<32, KC, 1>(P, grid, st);
+      case 64: return launch_cfg<64, KC, 1>(P, grid, st);
+      case 128: return launch_cfg<128, KC, 1>(P, grid, st);
+      case 256: return launch_cfg<256, KC, 1>(P, grid, st);
+    }
   }
-  disco_set_error("conv_tc: unsupported BN %d", BN);
+  disco_set_error("conv_tc: unsupported BN %d / MT %d", BN, MT);
   return DISCO_ERR_INVALID;
 }
 
@@ -1169,6 +1193,8 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   if (!env_read) {
     const char* e = getenv("DISCO_TC_RESIDENT");
     if (e && e[0] == '0') g_allow_resident = false;
+    const char* m2 = getenv("DISCO_TC_MT2");
+    if (m2 && m2[0] == '0') g_allow_mt2 = false;
     const char* hm = getenv("DISCO_TC_HALO");
     if (hm) g_halo_mode = atoi(hm);
     env_read = true;
@@ -1281,9 +1307,9 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     }
   } else {
     switch (c.plan.KC) {
-      case 64: rc = launch_bn<64>(c.plan.BN, c.params, c.grid, st); break;
-      case 32: rc = launch_bn<32>(c.plan.BN, c.params, c.grid, st); break;
-      case 16: rc = launch_bn<16>(c.plan.BN, c.params, c.grid, st); break;
+      case 64: rc = launch_bn<64>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
+      case 32: rc = launch_bn<32>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
+      case 16: rc = launch_bn<16>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
       default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
     }
   }
