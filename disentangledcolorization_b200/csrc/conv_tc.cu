@@ -39,6 +39,7 @@ namespace {
 
 constexpr int kMaxTaps = 24;
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreadsRes = 352;  // resident kernel: + warp 10 = second MMA issuer
 constexpr long long kSpinCycles = 6000000000ll;   // mbarrier wait watchdog (~3 s) -> trap instead of hanging the GPU
 
 struct Tap {
@@ -71,6 +72,7 @@ struct TcParams {
   int32_t nsteps[4];
   int32_t wkb_phase0[4];      // first weight K-block of each phase in the packed matrix
   int32_t res_stages, res_a_stage_bytes, res_b_bytes;
+  int32_t res_dual;           // 1: two MMA issuers alternate tiles (only when their pipeline-stage sets are disjoint)
   int32_t halo_bo_mask;       // 0: A descriptors carry base_offset 0; else mask applied to (start_addr >> 7)
   int32_t ntaps[4];
   int32_t kblocks[4];         // K-blocks per phase
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // Shared-memory layout: [stages x A stage][resident weights][barriers][epilogue parameter caches].
 // ------------------------------------------------------------------------------------------------
 template <int BN, int KC>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_constant__ TcParams P) {
+__global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __grid_constant__ TcParams P) {
   constexpr int B_BYTES = BN * KC * 2;
   constexpr int MAX_ST = 8;
   extern __shared__ uint8_t smem_raw[];
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     mbar_init(bfull, 1);
-    mbar_init(bempty, 1);
+    mbar_init(bempty, P.res_dual ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -718,9 +720,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (elect_one()) {
+  } else if (warp == 1 || warp == 10) {
+    // ===================================================================== MMA issuers (two, alternating tiles)
+    // Issuer r owns the CTA's tiles with local index parity r (= TMEM accumulator stage r).  While one issuer sits in
+    // its mbarrier waits / loop bookkeeping (~1000 cycles per tile, comparable to the 1700-cycle MMA batch of an
+    // N = 64 tile) the other one's MMAs keep the tensor pipe busy.
+    const int r = warp == 1 ? 0 : 1;
+    const bool dual = P.res_dual != 0;
+    // Two issuers are only safe when they never share a pipeline stage (an mbarrier waiter must not run a whole
+    // phase ahead of the barrier): the host enables `res_dual` iff stages % (2 * steps_per_tile) == 0.
+    if ((dual || r == 0) && elect_one()) {
       constexpr uint32_t idesc = instr_desc<BN>();
       constexpr int NK = KC / 16;
       const uint64_t desc_hi_lo = make_smem_desc<KC>(0);          // all fields except the start address
@@ -728,64 +737,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_res_kernel(const __grid_c
       const uint32_t desc_hi_fixed = (uint32_t)(desc_hi_lo >> 32) & ~0x3fffu;   // version + swizzle mode
       const uint32_t b_hi = (uint32_t)(desc_hi_lo >> 32);
       const uint32_t b_lo0 = (b_base >> 4) | 0x10000u;
-      uint32_t stage = 0, ph = 0, as = 0, aph = 0, bfph = 0;
+      uint32_t stage = 0, ph = 0, aph = 0, bfph = 0;
       int cur_phase = -1;
       const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
       int32_t* const perr = P.error_flag;
       TileIter it;
       it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
+      int li = 0;                                                   // local tile index
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB), ++li) {
         const int phase = it.phase;
+        const int ns = s_nsteps[phase];
+        const bool mine = dual ? ((li & 1) == r) : true;
         if (phase != cur_phase) {
           mbar_wait(bfull, bfph, perr);
           bfph ^= 1;
           cur_phase = phase;
         }
-        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 0);
-        mbar_wait(&tempty[as], aph ^ 1, perr);
-        tc_fence_after();
-        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 1);
-        const uint32_t d_tmem = tmem_base + as * BN;
-        const int ns = s_nsteps[phase];
-        uint32_t acc = 0;
-        for (int i = 0; i < ns; ++i) {
-          const Step& sp = s_steps[phase * kMaxSteps + i];
-          mbar_wait(&full[stage], ph, perr);
+        if (mine) {
+          const int as = dual ? r : (li & 1);
+          const uint32_t apar = dual ? aph : (uint32_t)((li >> 1) & 1);
+          mbar_wait(&tempty[as], apar ^ 1, perr);
+          aph ^= 1;
           tc_fence_after();
-          dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 2 + i);
-          // Descriptors are assembled from 32-bit halves with one add per tap: the hi words (stride, version,
-          // swizzle mode) are loop invariants, the lo word is (smem address >> 4) | LBO.
-          const uint32_t sa_lo = ((a_base + stage * a_stage) >> 4) | 0x10000u;
-          const uint32_t a_hi = (sp.a_sbo16 & 0x3fffu) | desc_hi_fixed;
-          const int ntap = sp.ntap;
-          uint32_t nstage = stage + 1, nph = ph;
-          if (nstage == (uint32_t)stages) { nstage = 0; nph ^= 1; }
-          uint32_t tw[9];
+          const uint32_t d_tmem = tmem_base + as * BN;
+          uint32_t acc = 0;
+          for (int i = 0; i < ns; ++i) {
+            const Step& sp = s_steps[phase * kMaxSteps + i];
+            mbar_wait(&full[stage], ph, perr);
+            tc_fence_after();
+            // Descriptors are assembled from 32-bit halves with one add per tap: the hi words (stride, version,
+            // swizzle mode) are loop invariants, the lo word is (smem address >> 4) | LBO.
+            const uint32_t sa_lo = ((a_base + stage * a_stage) >> 4) | 0x10000u;
+            const uint32_t a_hi = (sp.a_sbo16 & 0x3fffu) | desc_hi_fixed;
+            const int ntap = sp.ntap;
+            uint32_t tw[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) tw[t] = sp.tap[t];
+            for (int t = 0; t < 9; ++t) tw[t] = sp.tap[t];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (t < ntap) {
-              const uint32_t a_lo = sa_lo + (tw[t] & 0xffffu);
-              const uint32_t b_lo = b_lo0 + (tw[t] >> 16) * (uint32_t)(B_BYTES >> 4);
+            for (int t = 0; t < 9; ++t) {
+              if (t < ntap) {
+                const uint32_t a_lo = sa_lo + (tw[t] & 0xffffu);
+                const uint32_t b_lo = b_lo0 + (tw[t] >> 16) * (uint32_t)(B_BYTES >> 4);
 #pragma unroll
-              for (int k = 0; k < NK; ++k) {
-                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
-                acc = 1;
+                for (int k = 0; k < NK; ++k) {
+                  umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
+                  acc = 1;
+                }
               }
             }
+            umma_commit(&empty[stage]);
+            if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
           }
-          umma_commit(&empty[stage]);
-          stage = nstage; ph = nph;
+          umma_commit(&tfull[as]);
+        } else {
+          // the other issuer's tile: only track which pipeline stages it consumes
+          for (int i = 0; i < ns; ++i)
+            if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);
-        dbg_stamp(P, 1, (tile - blockIdx.x) / gridDim.x, 7);
-        if (++as == 2) { as = 0; aph ^= 1; }
         const int next = tile + gridDim.x;
-        if (next < total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);
+        if (next < total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);   // both issuers (count 2)
       }
     }
-  } else {
+  } else if (warp < 10) {
     epilogue_role<BN>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
@@ -822,11 +835,13 @@ struct Plan {
   int spanx[2] = {0, 0};             // extra box columns (halo mode)
   bool halo = false;
   int res_stages = 0, res_a_stage_bytes = 0, res_b_bytes = 0, res_smem_bytes = 0;
+  bool res_dual = false;
 };
 
 int pow2_ceil_(int v) { int p = 1; while (p < v) p *= 2; return p; }
 bool g_allow_resident = true;
 bool g_allow_mt2 = true;
+bool g_allow_dual = true;
 int g_halo_mode = 1;                 // 0 off, 1 halo tiles (descriptor base_offset 0: the hardware swizzle is a function of
                                      // the absolute smem address -- verified on B200), 2 = experiment: base_offset from addr bits (wrong)
 
@@ -1032,6 +1047,17 @@ Plan build_plan(const disco_conv_desc* d) {
   int stages = (225 * 1024 - fixed) / a_stage;
   if (stages > 8) stages = 8;
   if (stages < 2) return p;
+  // dual MMA issuers: all phases must have the same number of steps per tile and the stage ring must split evenly
+  {
+    int ns0 = p.nsteps[0];
+    bool same = true;
+    for (int ph = 1; ph < p.n_phase; ++ph) same = same && p.nsteps[ph] == ns0;
+    p.res_dual = false;
+    if (g_allow_dual && same && ns0 >= 1 && stages >= 2 * ns0) {
+      stages = stages / (2 * ns0) * (2 * ns0);
+      p.res_dual = true;
+    }
+  }
   p.resident = true;
   p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_bytes;
   p.res_smem_bytes = stages * a_stage + fixed;
@@ -1098,7 +1124,7 @@ int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st)
     DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes = smem_bytes;
   }
-  conv_tc_res_kernel<BN, KC><<<grid, kThreads, smem_bytes, st>>>(P);
+  conv_tc_res_kernel<BN, KC><<<grid, kThreadsRes, smem_bytes, st>>>(P);
   return DISCO_OK;
 }
 
@@ -1193,6 +1219,8 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   if (!env_read) {
     const char* e = getenv("DISCO_TC_RESIDENT");
     if (e && e[0] == '0') g_allow_resident = false;
+    const char* du = getenv("DISCO_TC_DUAL");
+    if (du && du[0] == '0') g_allow_dual = false;
     const char* m2 = getenv("DISCO_TC_MT2");
     if (m2 && m2[0] == '0') g_allow_mt2 = false;
     const char* hm = getenv("DISCO_TC_HALO");
@@ -1244,6 +1272,7 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     memcpy(P.nsteps, pl.nsteps, sizeof(P.nsteps));
     memcpy(P.wkb_phase0, pl.wkb_phase0, sizeof(P.wkb_phase0));
     P.res_stages = pl.res_stages; P.res_a_stage_bytes = pl.res_a_stage_bytes; P.res_b_bytes = pl.res_b_bytes;
+    P.res_dual = pl.res_dual ? 1 : 0;
     P.halo_bo_mask = (pl.halo && g_halo_mode == 2) ? (pl.KC == 64 ? 7 : (pl.KC == 32 ? 3 : 1)) : 0;
     P.TW = TW; P.TH = TH; P.NB = NB; P.tw_log2 = ilog2(TW); P.th_log2 = ilog2(TH);
     P.tiles_x = (P.Wg + TW - 1) / TW; P.tiles_y = (P.Hg + TH - 1) / TH; P.tiles_b = (P.B + NB - 1) / NB;

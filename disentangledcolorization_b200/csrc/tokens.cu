@@ -319,7 +319,7 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
 
 // mode 0: grid B, speculative (draw offset 0).  mode 1: grid 1, sequential fix-up in image order.
 // Dynamic shared memory (when it fits): transposed tokens XT[64][S+1] followed by int assign[S].
-__global__ void __launch_bounds__(256) kmeans_anchor_kernel(const KmArgs a, int mode, int use_smem) {
+__global__ void __launch_bounds__(512) kmeans_anchor_kernel(const KmArgs a, int mode, int use_smem) {
   __shared__ float C[KMAX * KD];
   __shared__ float Cprev[KMAX * KD];
   __shared__ int cnt[KMAX];
@@ -465,9 +465,9 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   const int use_smem = dyn <= 160 * 1024;
   if (use_smem && dyn > 32 * 1024)
     DISCO_CUDA(cudaFuncSetAttribute(kmeans_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  kmeans_anchor_kernel<<<batch, 256, use_smem ? dyn : 0, st>>>(a, 0, use_smem);
+  kmeans_anchor_kernel<<<batch, 512, use_smem ? dyn : 0, st>>>(a, 0, use_smem);
   DISCO_LAUNCH_CHECK(h);
-  kmeans_anchor_kernel<<<1, 256, use_smem ? dyn : 0, st>>>(a, 1, use_smem);
+  kmeans_anchor_kernel<<<1, 512, use_smem ? dyn : 0, st>>>(a, 1, use_smem);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }
