@@ -18,7 +18,7 @@ EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy",
            "disco_reset_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
-           "disco_debug_timeline", "disco_token_sample3"]
+           "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail"]
 
 
 class ConvSrc(C.Structure):
@@ -83,6 +83,7 @@ def load():
                                        C.c_void_p, C.c_void_p]
     lib.disco_token_sample3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
+    lib.disco_encoder_tail.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 11
     _lib = lib
     return lib
 

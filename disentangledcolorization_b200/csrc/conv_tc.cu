@@ -365,6 +365,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
         }
       }
     }
+    // residual of the first column chunk: issued before the accumulator wait so its latency hides behind the MMAs
+    uint4 rpre[CH / 8];
+    if (pres != nullptr && valid && n0 + col0 < pCout) {
+      const uint4* rp = reinterpret_cast<const uint4*>(pres + pix * pCout + n0 + col0);
+#pragma unroll
+      for (int u = 0; u < CH / 8; ++u) rpre[u] = __ldg(rp + u);
+    }
     if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 0);
     mbar_wait(&tfull[as], aph, perr);
     tc_fence_after();
@@ -400,7 +407,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
               const uint4* rp = reinterpret_cast<const uint4*>(pres + pix * pCout + n0 + c0);
 #pragma unroll
               for (int u = 0; u < CH / 8; ++u) {
-                const uint4 rr = __ldg(rp + u);
+                const uint4 rr = (c0 == col0) ? rpre[u] : __ldg(rp + u);
                 const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

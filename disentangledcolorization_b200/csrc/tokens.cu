@@ -109,6 +109,144 @@ __global__ void __launch_bounds__(256) linear_kernel(const disco_linear_desc d) 
 }
 
 // ------------------------------------------------------------------------------------------
+// fused encoder-layer tail: y = LN2(x1 + W2 relu(W1 x1 + b1) + b2),  x1 = LN1(x + Wo att + bo)
+// (EncoderLayer.forward after the attention core, models/transformer2d.py:55-59).  One CTA = 64 tokens, 256 threads,
+// 4x4 register micro-tiles; x1 and the 256-wide hidden activations never leave shared memory (stored k-major so
+// they feed the next GEMM directly); weights stream through a 16-deep shared-memory tile.
+// ------------------------------------------------------------------------------------------
+struct EncTailArgs {
+  const float* att; const float* x; float* y; int M;
+  const float* wo; const float* bo; const float* g1; const float* be1;
+  const float* w1; const float* b1; const float* w2; const float* b2; const float* g2; const float* be2;
+};
+
+__device__ __forceinline__ void mm_chunk(const float (*Ak)[68], int k0, const float (*Bs)[68], int tx, int ty, float (&acc)[4][4]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float4 av = *reinterpret_cast<const float4*>(&Ak[k0 + k][ty * 4]);
+    const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const float aa[4] = {av.x, av.y, av.z, av.w};
+    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+  }
+}
+
+// LayerNorm over the 64 columns of each of the 64 rows held in Cs; result written k-major into XT and (optionally) to global
+__device__ __forceinline__ void ln_rows(float (*Cs)[65], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        float (*XT)[68], float* __restrict__ gout, int m0, int M, int tid) {
+  if (tid < 64) {
+    float mean = 0.f;
+    for (int c = 0; c < 64; ++c) mean += Cs[tid][c];
+    mean *= (1.f / 64.f);
+    float var = 0.f;
+    for (int c = 0; c < 64; ++c) { const float t = Cs[tid][c] - mean; var = fmaf(t, t, var); }
+    var *= (1.f / 64.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int c = 0; c < 64; ++c) Cs[tid][c] = (Cs[tid][c] - mean) * rstd * gamma[c] + beta[c];
+  }
+  __syncthreads();
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (XT) XT[c][r] = Cs[r][c];
+    if (gout && m0 + r < M) gout[(size_t)(m0 + r) * 64 + c] = Cs[r][c];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) encoder_tail_kernel(const EncTailArgs a) {
+  extern __shared__ float et_smem[];
+  float (*X1T)[68] = reinterpret_cast<float (*)[68]>(et_smem);                    // [64 k][68]  x1, k-major
+  float (*HdT)[68] = reinterpret_cast<float (*)[68]>(et_smem + 64 * 68);          // [256 k][68] hidden, k-major
+  float (*As)[68] = reinterpret_cast<float (*)[68]>(et_smem + (64 + 256) * 68);   // [16][68]
+  float (*Bs)[68] = reinterpret_cast<float (*)[68]>(et_smem + (64 + 256 + 16) * 68);
+  float (*Cs)[65] = reinterpret_cast<float (*)[65]>(et_smem + (64 + 256 + 32) * 68);   // [64][65]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 64;
+  const int lr = tid >> 2, lc = (tid & 3) * 4;   // load role: row lr, k offset lc..lc+3
+  float acc[4][4];
+
+  // ---- phase 1: x1 = LN1(x + att Wo^T + bo)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < 64; k0 += 16) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + lr < a.M) v = *reinterpret_cast<const float4*>(a.att + (size_t)(m0 + lr) * 64 + k0 + lc);
+    As[lc + 0][lr] = v.x; As[lc + 1][lr] = v.y; As[lc + 2][lr] = v.z; As[lc + 3][lr] = v.w;
+    const float4 wv = *reinterpret_cast<const float4*>(a.wo + (size_t)lr * 64 + k0 + lc);
+    Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
+    __syncthreads();
+    mm_chunk(As, 0, Bs, tx, ty, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tx * 4 + j;
+      float v = acc[i][j] + a.bo[c];
+      if (m0 + r < a.M) v += a.x[(size_t)(m0 + r) * 64 + c];
+      Cs[r][c] = v;
+    }
+  }
+  __syncthreads();
+  ln_rows(Cs, a.g1, a.be1, X1T, nullptr, m0, a.M, tid);
+
+  // ---- phase 2: hidden = relu(x1 W1^T + b1), four 64-column blocks
+  for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < 64; k0 += 16) {
+      const float4 wv = *reinterpret_cast<const float4*>(a.w1 + (size_t)(nb * 64 + lr) * 64 + k0 + lc);
+      Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
+      __syncthreads();
+      mm_chunk(X1T, k0, Bs, tx, ty, acc);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = nb * 64 + tx * 4 + j;
+        const float v = acc[i][j] + a.b1[c];
+        HdT[c][ty * 4 + i] = v > 0.f ? v : 0.f;
+      }
+  }
+  __syncthreads();
+
+  // ---- phase 3: y = LN2(x1 + hidden W2^T + b2)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < 256; k0 += 16) {
+    const float4 wv = *reinterpret_cast<const float4*>(a.w2 + (size_t)lr * 256 + k0 + lc);
+    Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
+    __syncthreads();
+    mm_chunk(HdT, k0, Bs, tx, ty, acc);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = tx * 4 + j;
+      Cs[r][c] = acc[i][j] + a.b2[c] + X1T[c][r];
+    }
+  }
+  __syncthreads();
+  ln_rows(Cs, a.g2, a.be2, nullptr, a.y, m0, a.M, tid);
+}
+
+// ------------------------------------------------------------------------------------------
 // attention core: grid (B*8, ceil(S/128)), 128 threads, thread = query; K/V of the head in smem.
 // One pass over the keys with a running maximum (online softmax, fp32), four keys per iteration for ILP.
 // ------------------------------------------------------------------------------------------
@@ -152,6 +290,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     const float4 a = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8);
     const float4 b = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8 + 4);
     q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    // scores are kept in log2 units so that the softmax exponentials are single ex2 instructions
+#pragma unroll
+    for (int c = 0; c < 8; ++c) q[c] *= 1.4426950408889634f;
   }
   float mx = -FLT_MAX, sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < S4; j += 4) {
@@ -162,8 +303,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
       s3 = -FLT_MAX;
     }
     const float mnew = fmaxf(fmaxf(mx, fmaxf(s0, s1)), fmaxf(s2, s3));
-    const float corr = expf(mx - mnew);
-    const float p0 = expf(s0 - mnew), p1 = expf(s1 - mnew), p2 = expf(s2 - mnew), p3 = expf(s3 - mnew);
+    const float corr = exp2f(mx - mnew);
+    const float p0 = exp2f(s0 - mnew), p1 = exp2f(s1 - mnew), p2 = exp2f(s2 - mnew), p3 = exp2f(s3 - mnew);
     sum = fmaf(sum, corr, (p0 + p1) + (p2 + p3));
 #pragma unroll
     for (int c = 0; c < 8; ++c) o[c] *= corr;
@@ -436,6 +577,23 @@ extern "C" int disco_linear(disco_handle* h, const disco_linear_desc* d, void* s
   DISCO_CHECK_ARG(!d->hint_mask || (d->labels && d->emb), "linear: hint embedding needs labels and emb");
   dim3 grid((d->M + LT - 1) / LT, (d->N + LT - 1) / LT);
   linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}
+
+extern "C" int disco_encoder_tail(disco_handle* h, const float* att, const float* x, float* y, int M, const float* wo,
+                                  const float* bo, const float* ln1_g, const float* ln1_b, const float* w1, const float* b1,
+                                  const float* w2, const float* b2, const float* ln2_g, const float* ln2_b, void* stream) {
+  DISCO_CHECK_ARG(h && att && x && y && wo && bo && ln1_g && ln1_b && w1 && b1 && w2 && b2 && ln2_g && ln2_b && M > 0,
+                  "encoder_tail: bad argument");
+  const EncTailArgs a{att, x, y, M, wo, bo, ln1_g, ln1_b, w1, b1, w2, b2, ln2_g, ln2_b};
+  const int smem = ((64 + 256 + 32) * 68 + 64 * 65) * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    DISCO_CUDA(cudaFuncSetAttribute(encoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  encoder_tail_kernel<<<(M + 63) / 64, 256, smem, (cudaStream_t)stream>>>(a);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }

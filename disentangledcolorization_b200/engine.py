@@ -286,10 +286,11 @@ class Engine:
                          col_scale=8 ** -0.5, scale_cols=64)
             _lib.check(self.lib.disco_attention(self.handle.h, _ptr(tok["qkv"]), B, S, _ptr(tok["att"]), stream),
                        "disco_attention")
-            self._linear(stream, tok["att"], L["out_w"], tok["x1"], b=L["out_b"], residual=x, ln=(L["n1_w"], L["n1_b"]))
-            self._linear(stream, tok["x1"], L["l1_w"], tok["hid"], b=L["l1_b"], relu=True)
             y = out if i == len(layers) - 1 else (tok["xa"] if i % 2 == 0 else tok["xb"])
-            self._linear(stream, tok["hid"], L["l2_w"], y, b=L["l2_b"], residual=tok["x1"], ln=(L["n2_w"], L["n2_b"]))
+            _lib.check(self.lib.disco_encoder_tail(self.handle.h, _ptr(tok["att"]), _ptr(x), _ptr(y), x.shape[0],
+                                                   _ptr(L["out_w"]), _ptr(L["out_b"]), _ptr(L["n1_w"]), _ptr(L["n1_b"]),
+                                                   _ptr(L["l1_w"]), _ptr(L["l1_b"]), _ptr(L["l2_w"]), _ptr(L["l2_b"]),
+                                                   _ptr(L["n2_w"]), _ptr(L["n2_b"]), stream), "disco_encoder_tail")
             x = y
 
     # ------------------------------------------------------------------ RNG protocol

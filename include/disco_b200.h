@@ -152,6 +152,12 @@ typedef struct {
 } disco_linear_desc;
 int disco_linear(disco_handle* h, const disco_linear_desc* d, void* stream);
 
+/* Fused tail of one EncoderLayer (models/transformer2d.py:55-59): x1 = LayerNorm1(x + att Wo^T + bo);
+ * y = LayerNorm2(x1 + W2 relu(W1 x1 + b1) + b2).  att, x, y: fp32 [M,64]; Wo [64,64]; W1 [256,64]; W2 [64,256]. */
+int disco_encoder_tail(disco_handle* h, const float* att, const float* x, float* y, int M, const float* wo,
+                       const float* bo, const float* ln1_g, const float* ln1_b, const float* w1, const float* b1,
+                       const float* w2, const float* b2, const float* ln2_g, const float* ln2_b, void* stream);
+
 /* Multi-head self-attention core: softmax(q k^T) v per (image, head); q already scaled.
  * Replaces the attention inside nn.MultiheadAttention (models/transformer2d.py:36,54).
  *   qkv [B*S, 192] (q | k | v, head h = columns 8h..8h+7 of each third) -> out [B*S, 64] */
