@@ -15,7 +15,7 @@ HEAD_NONE, HEAD_SOFTMAX9, HEAD_TANH2 = 0, 1, 2
 CONV3, DECONV4 = 0, 1
 
 EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
-           "disco_reset_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
+           "disco_reset_launch_count", "disco_add_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
            "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail"]
@@ -65,6 +65,7 @@ def load():
     lib.disco_launch_count.restype = C.c_int64
     lib.disco_launch_count.argtypes = [C.c_void_p]
     lib.disco_reset_launch_count.argtypes = [C.c_void_p]
+    lib.disco_add_launch_count.argtypes = [C.c_void_p, C.c_int64]
     lib.disco_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
     lib.disco_destroy.argtypes = [C.c_void_p]
     lib.disco_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p]

@@ -46,6 +46,7 @@ extern "C" int disco_destroy(disco_handle* h) {
 
 extern "C" int64_t disco_launch_count(disco_handle* h) { return h ? h->launches : -1; }
 extern "C" void disco_reset_launch_count(disco_handle* h) { if (h) h->launches = 0; }
+extern "C" void disco_add_launch_count(disco_handle* h, int64_t n) { if (h) h->launches += n; }
 
 extern "C" int disco_conv(disco_handle* h, const disco_conv_desc* d, void* stream) {
   DISCO_CHECK_ARG(h && d, "conv: null handle/descriptor");

@@ -37,6 +37,13 @@ class AnchorColorProb(nn.Module):
 
     #: 'bf16' = tensor-core path (bf16 storage, fp32 accumulate); 'fp32' = exact CUDA-core path
     precision = "bf16"
+    #: replay the forward from a CUDA graph (one graph per input shape; sampled_T == 0 only).  Off by default:
+    #: the CLI feeds images of arbitrary sizes one at a time; batch serving with fixed shapes should turn it on.
+    use_cuda_graph = False
+    #: graph mode only: return the graph-owned output tensors (overwritten by the next forward) instead of copies
+    graph_static_outputs = False
+    #: defer the host-RNG fix-up (one tiny D2H read + sync) to the next forward / engine().sync_rng()
+    lazy_rng = False
 
     def __init__(self, inChannel=1, outChannel=313, sp_size=16, d_model=64, use_dense_pos=True, spix_pos=False,
                  learning_pos=False, n_clusters=8, random_hint=False, hint2regress=False, enhanced=False,
@@ -117,6 +124,9 @@ class AnchorColorProb(nn.Module):
             self._engine = Engine(self.state_dict(), device, precision=self.precision, n_clusters=self.hint_num,
                                   sp_size=self.sp_size, enhanced=self.enhanced, random_hint=self.random_hint)
             self._engine_key = key
+        self._engine.use_graph = self.use_cuda_graph
+        self._engine.static_outputs = self.graph_static_outputs
+        self._engine.lazy_rng = self.lazy_rng
         return self._engine
 
     def forward(self, input_grays, input_colors, test_mode=False, sampled_T=0, hint_mask=None, init_idx=None):

@@ -47,6 +47,8 @@ int disco_destroy(disco_handle* h);
 /* number of kernel launches issued through this handle since creation / last reset */
 int64_t disco_launch_count(disco_handle* h);
 void disco_reset_launch_count(disco_handle* h);
+/* accounts for kernels replayed from a CUDA graph that was captured from calls on this handle */
+void disco_add_launch_count(disco_handle* h, int64_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused convolution.  Replaces every nn.Conv2d / nn.ConvTranspose2d (+ bias, activation,
