@@ -237,8 +237,19 @@ def run_ours(args):
         # per-launch timing of the conv kernel family (extra steps, CUDA events around every disco_conv)
         prof = eng.profile_convs(gray, ab, steps=2)
         conv_flops, conv_ms = prof["flops"], prof["ms"]
-        achieved = conv_flops / (conv_ms / 1e3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        fam_achieved = conv_flops / (conv_ms / 1e3) / 1e12
+        # dominant kernel: the streaming tcgen05 kernel instantiated for 256-column tiles = every conv with Cout >= 256
+        # (27 launches per step, the largest share of device time in profiles/r1_launches_summary.md)
+        dom = [(k, v) for k, v in prof["per_op"].items() if v.get("cout", 0) >= 256]
+        dom_ms = sum(v["ms"] for _, v in dom)
+        dom_flops = sum(v["flops"] for _, v in dom)
+        achieved = dom_flops / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)["bytes"].get("r1_c512")
         log("conv profile done")
         if args.dump_profile:
             with open(args.dump_profile, "w") as f:
@@ -260,10 +271,16 @@ def run_ours(args):
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "kernel": "disco_conv (all conv launches of one step)",
-                         "peak_source": f"{which} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
-                         "conv_share_of_step": conv_ms / (ms / args.steps),
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "conv_tc_kernel<256,64,1> (tcgen05 implicit GEMM; all conv launches with Cout >= 256)",
+                         "launches_per_step": len(dom), "kernel_ms_per_step": dom_ms,
+                         "kernel_share_of_step": dom_ms / (ms / args.steps),
+                         "algorithmic_flops_per_launch": "2*B*Ho*Wo*Cin*Cout*9 (reference formulation)",
+                         "traffic_note": "dram read+write bytes of one 512->512@32x32 launch (profiles/r1_c512_ncu_raw.csv); "
+                                         "algorithmic bytes of that launch: 139e6",
+                         "peak_source": f"{which} bf16_tflops_sustained",
+                         "conv_family": {"achieved": fam_achieved, "frac": fam_achieved / peak, "ms_per_step": conv_ms,
+                                         "share_of_step": conv_ms / (ms / args.steps)},
                          "whole_step_frac": (B * FLOP_PER_IMAGE / (ms / args.steps / 1e3) / 1e12) / peak,
                          "top": prof["top"]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",

@@ -520,13 +520,14 @@ class Engine:
             f = self.algorithmic_flops(op, B, Ho, Wo)
             flops += f
             ms += t
-            a = per_op.setdefault(op.name, [0.0, 0.0])
+            a = per_op.setdefault(op.name, [0.0, 0.0, op.cout])
             a[0] += f
             a[1] += t
         top = sorted(per_op.items(), key=lambda kv: -kv[1][1])[:6]
         return {"flops": flops / steps, "ms": ms / steps,
                 "top": [{"op": k, "ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12} for k, v in top],
-                "per_op": {k: {"ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12} for k, v in per_op.items()}}
+                "per_op": {k: {"ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12, "flops": v[0] / steps, "cout": v[2]}
+                           for k, v in per_op.items()}}
 
     def kmeans_iterations(self, B, H, W):
         return self._ws[(B, H, W)]["tok"]["iters"].cpu()
