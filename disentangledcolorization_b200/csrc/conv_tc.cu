@@ -56,10 +56,12 @@ struct Tap {
 // filter taps (the taps of one filter column: same dx, dy = -1,0,+1 -> the box carries TH+2 rows and each tap's
 // A operand starts `dy*TW` rows further down, which keeps the start address on a swizzle-atom boundary).
 struct Step {
-  int8_t src, mode, ox, oy, py, px, ntap, pad;
+  int8_t src, mode, ox, oy, py, px, ntap;
+  int8_t nch;          // grouped streaming kernel: input-channel chunks this step iterates over (resident kernel: 1)
   int32_t c0;          // inner-dimension start coordinate (channel chunk, + px*C for the stride-2 view)
   uint32_t bytes;      // bytes the load delivers
   uint32_t a_sbo16;    // byte distance between 8-row groups of the A operand, >> 4 (halo tiles: (TW+2) pixels)
+  uint32_t mt_off16;   // byte distance between the two 128-pixel sub-tiles of a 256-pixel tile inside the box, >> 4
   uint32_t tap[9];     // (A start offset in bytes >> 4) | (resident weight block index << 16)
 };
 constexpr int kMaxSteps = 16;
@@ -72,6 +74,7 @@ struct TcParams {
   int32_t nsteps[4];
   int32_t wkb_phase0[4];      // first weight K-block of each phase in the packed matrix
   int32_t res_stages, res_a_stage_bytes, res_b_bytes;
+  int32_t grp_b_stages;       // grouped streaming kernel: weight-tile ring depth (res_stages = activation-box ring depth)
   int32_t res_dual;           // 1: two MMA issuers alternate tiles (only when their pipeline-stage sets are disjoint)
   int32_t halo_bo_mask;       // 0: A descriptors carry base_offset 0; else mask applied to (start_addr >> 7)
   int32_t ntaps[4];
@@ -155,6 +158,48 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: loads land in the executing CTA's shared memory, the transaction bytes are
+// signalled on the LEADER CTA's mbarrier (`bar_cluster` = shared::cluster address obtained with mapa)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -205,6 +250,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// cta_group::2: one instruction multiplies the 256 x K operand held as two 128-row halves (one per CTA of the pair) with
+// the N x K operand held as two N/2-row halves; each CTA's tensor memory receives its own 128 accumulator rows.
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -240,19 +302,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-template <int BN>
+template <int BN, int M = 128>
 __host__ __device__ constexpr uint32_t instr_desc() {
   // c_format f32 [4,6)=1, a/b format bf16 [7,10)/[10,13)=1, K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int KC, int MT = 1>
+template <int BN, int KC, int MT = 1, bool PAIR = false>
 struct Cfg {
   // MT = 128-pixel sub-tiles per CTA tile.  MT = 2 (narrow N <= 128 tiles only): one TMA box brings 256 pixels and
   // both halves are multiplied against the SAME weight tile, which halves the weight traffic per MAC -- N = 128
   // tiles at 125 B/clk/SM of operand fill are otherwise bound by the L2->SM fabric (~107 B/clk/SM measured).
   static constexpr int A_BYTES = 128 * MT * KC * 2;
-  static constexpr int B_BYTES = BN * KC * 2;
+  // PAIR: the two CTAs of a cluster run cta_group::2 MMAs (M = 256) on two horizontally adjacent pixel tiles; each
+  // CTA stages only HALF of the weight tile (BN/2 rows), which halves the weight L2->SMEM fill and the B-operand
+  // shared-memory reads per MMA (N = 128 tiles are otherwise bound by the 128 B/clk shared-memory read port).
+  static constexpr int B_BYTES = BN * KC * 2 / (PAIR ? 2 : 1);
   // K-blocks per pipeline stage: with MT = 1 narrow tiles finish a K-block's MMAs in <= 256 cycles, which does not
   // cover an mbarrier round trip, so two K-blocks share one stage / one full-empty handshake
   static constexpr int KB = (BN <= 128 && MT == 1) ? 2 : 1;
@@ -299,9 +364,15 @@ struct TileIter {
 // Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
 // lane quarter (w & 3) (a hardware restriction) and, when BN >= 32, the column half ((w - 2) >> 2): two warps per
 // SM sub-partition keep the epilogue's issue rate up (one warp alone runs at IPC ~0.2 on dependent fp32 math).
-template <int BN, int MT = 1>
+template <int BN, int MT = 1, bool PAIR = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                               float* epi_params, int warp, int lane) {
+  // PAIR: this CTA owns pixel-tile column 2*xt + rank of the cluster's tile pair; accumulator-free signals go to the
+  // leader CTA's barrier (the only MMA issuer of the pair)
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int gdim = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(tempty), 0) : 0;
   constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
   // MT == 1: the two warps of a lane quarter split the columns.  MT == 2: they take one 128-pixel sub-tile each.
@@ -329,11 +400,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   int cached_nt = -1;
   uint32_t as = 0, aph = 0;
   TileIter it;
-  it.init(P, blockIdx.x, gridDim.x);
+  it.init(P, bid, gdim);
   const int tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
-  for (int tile = blockIdx.x; tile < ptotal; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
+  for (int tile = bid; tile < ptotal; tile += gdim, it.next(tn, tX, tY, tB)) {
     const int phase = it.phase, nt = it.nt;
-    const int X = it.xt * pTW + tx, Y = it.yt * pTH + ty, b = it.bt * pNB + nb;
+    const int X = (PAIR ? 2 * it.xt + crank : it.xt) * pTW + tx, Y = it.yt * pTH + ty, b = it.bt * pNB + nb;
     const bool valid = active && X < pWg && Y < pHg && b < pB;
     const int oy = Y * pos + (phase >> 1), ox = X * pos + (phase & 1);
     const size_t pix = ((size_t)b * pHo + oy) * pWo + ox;
@@ -372,10 +443,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 #pragma unroll
       for (int u = 0; u < CH / 8; ++u) rpre[u] = __ldg(rp + u);
     }
-    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 0);
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 0);
     mbar_wait(&tfull[as], aph, perr);
     tc_fence_after();
-    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 1);
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 1);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (MT * BN) + sub * BN;
     if (phead == DISCO_HEAD_NONE) {
       if (active && P.dbg_mode != 1) {
@@ -500,15 +571,23 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[as]);
-    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - blockIdx.x) / gridDim.x, 2);
+    if (lane == 0) {
+      if constexpr (PAIR) mbar_arrive_cluster(tempty_leader + 8 * as);
+      else mbar_arrive(&tempty[as]);
+    }
+    if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 2);
     if (++as == 2) { as = 0; aph ^= 1; }
   }
 }
 
-template <int BN, int KC, int MT>
+template <int BN, int KC, int MT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
-  using C = Cfg<BN, KC, MT>;
+  using C = Cfg<BN, KC, MT, PAIR>;
+  // PAIR: launched as clusters of two CTAs; cluster c works on tile pairs c, c + #clusters, ... (P.tiles_x and
+  // P.tiles_total count PAIRS of horizontally adjacent pixel tiles)
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int gdim = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                        // [stage][KB] A tiles
@@ -531,17 +610,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      // issued by the same warp of both CTAs; both receive the same column range
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -549,11 +637,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ===================================================================== TMA producer
     if (elect_one()) {
       uint32_t stage = 0, ph = 0;
+      const uint32_t full_leader = PAIR ? mapa_u32(smem_u32(full), 0) : 0;
+      const bool skip_a = P.dbg_mode == 3, skip_b = P.dbg_mode == 4;     // experiments: operand fill switched off
+      const uint32_t stage_tx = (skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES);
       TileIter it;
-      it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+      it.init(P, bid, gdim);
+      for (int tile = bid; tile < P.tiles_total; tile += gdim, it.next(P)) {
         const int phase = it.phase, nt = it.nt;
-        const int x0 = it.xt * P.TW, y0 = it.yt * P.TH, b0 = it.bt * P.NB;
+        const int x0 = (PAIR ? 2 * it.xt + crank : it.xt) * P.TW, y0 = it.yt * P.TH, b0 = it.bt * P.NB;
         const int ntap = P.ntaps[phase];
         int sub = 0;                        // K-blocks already issued into the current stage
         int left = P.kblocks[phase];        // K-blocks of this tile not yet issued
@@ -563,15 +654,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (sub == 0) {
               mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
               const int n = left < C::KB ? left : C::KB;
-              mbar_expect_tx(&full[stage], (uint32_t)(n * (C::A_BYTES + C::B_BYTES)));
+              // PAIR: the leader's barrier collects the bytes of both CTAs' loads
+              if (!PAIR || crank == 0) mbar_expect_tx(&full[stage], (uint32_t)((PAIR ? 2 : 1) * n) * stage_tx);
             }
             void* da = smem_a + (stage * C::KB + sub) * C::A_BYTES;
             void* db = smem_b + (stage * C::KB + sub) * C::B_BYTES;
-            if (tp.mode == 0)
-              tma_load_4d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, y0 + tp.oy, b0);
-            else
-              tma_load_5d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, tp.py, y0 + tp.oy, b0);
-            tma_load_2d(db, &P.tmB, &full[stage], 0, (tp.wkb0 + ch) * P.cout_pad + nt * BN);
+            if constexpr (PAIR) {
+              const uint32_t fb = full_leader + 8 * stage;
+              if (skip_a) {
+              } else if (tp.mode == 0)
+                tma2_load_4d(da, &P.tmA[tp.src], fb, tp.c_base + ch * KC, x0 + tp.ox, y0 + tp.oy, b0);
+              else
+                tma2_load_5d(da, &P.tmA[tp.src], fb, tp.c_base + ch * KC, x0 + tp.ox, tp.py, y0 + tp.oy, b0);
+              if (!skip_b) tma2_load_2d(db, &P.tmB, fb, 0, (tp.wkb0 + ch) * P.cout_pad + nt * BN + crank * (BN / 2));
+            } else {
+              if (skip_a) {
+              } else if (tp.mode == 0)
+                tma_load_4d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, y0 + tp.oy, b0);
+              else
+                tma_load_5d(da, &P.tmA[tp.src], &full[stage], tp.c_base + ch * KC, x0 + tp.ox, tp.py, y0 + tp.oy, b0);
+              if (!skip_b) tma_load_2d(db, &P.tmB, &full[stage], 0, (tp.wkb0 + ch) * P.cout_pad + nt * BN);
+            }
             --left;
             if (++sub == C::KB || left == 0) {
               sub = 0;
@@ -582,19 +685,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc<BN>();
+    // ===================================================================== MMA issuer (PAIR: leader CTA only)
+    if ((!PAIR || crank == 0) && elect_one()) {
+      constexpr uint32_t idesc = instr_desc<BN, PAIR ? 256 : 128>();
       constexpr int NK = KC / 16;
       const uint64_t desc0 = make_smem_desc<KC>(0);
-      const uint32_t a_base16 = smem_u32(smem_a) >> 4, b_base16 = smem_u32(smem_b) >> 4;
+      const uint32_t a_base16 = (smem_u32(smem_a) & 0x3FFFF) >> 4, b_base16 = (smem_u32(smem_b) & 0x3FFFF) >> 4;
       uint32_t stage = 0, ph = 0, as = 0, aph = 0;
       const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
       const int kbs[4] = {P.kblocks[0], P.kblocks[1], P.kblocks[2], P.kblocks[3]};
       int32_t* const perr = P.error_flag;
       TileIter it;
-      it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB)) {
+      it.init(P, bid, gdim);
+      for (int tile = bid; tile < total; tile += gdim, it.next(tn, tX, tY, tB)) {
         const int nkb = kbs[it.phase];
         mbar_wait(&tempty[as], aph ^ 1, perr);
         tc_fence_after();
@@ -610,27 +713,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                for (int k = 0; k < NK; ++k)
-                  umma_bf16(d_tmem + mt * BN, ad + mt * (128 * KC * 2 >> 4) + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+                for (int k = 0; k < NK; ++k) {
+                  if constexpr (PAIR)
+                    umma2_bf16(d_tmem + mt * BN, ad + mt * (128 * KC * 2 >> 4) + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+                  else
+                    umma_bf16(d_tmem + mt * BN, ad + mt * (128 * KC * 2 >> 4) + 2 * k, bd + 2 * k, idesc, (kb | sb | k) != 0);
+                }
               }
             }
           }
-          umma_commit(&empty[stage]);
+          if constexpr (PAIR) umma2_commit(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == (uint32_t)C::STAGES) { stage = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if constexpr (PAIR) umma2_commit(&tfull[as]); else umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else {
-    epilogue_role<BN, MT>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+    epilogue_role<BN, MT, PAIR>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // neither CTA leaves (or frees tensor memory) while the pair is still working
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
@@ -817,6 +928,193 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grouped streaming kernel for wide layers (Cout >= 128).  The plain streaming kernel above fills 16 KB of activations
+// per (tap, chunk) K-block; measured on B200 the L2->SM fill (64..80 B/clk/SM for these tiles), not the tensor pipe,
+// bounds it (switching the A fill off makes the same MMA stream 25..50 % faster).  Here ONE activation box with
+// a row halo (TH+2 rows; optionally also a column halo) serves the 3 (or all 9) taps that read it: the tap's A
+// descriptor simply starts `dy*row_pitch (+dx)` pixels further into the box.  Activations and weights travel in
+// separate rings (a box is consumed by several weight tiles): per step 1 box load + ntap weight-tile loads.
+//   PAIR: clusters of two CTAs, cta_group::2 MMAs (M = 256), each CTA stages half of every weight tile.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int KC, int MT, bool PAIR>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_grp_kernel(const __grid_constant__ TcParams P) {
+  constexpr int B_BYTES = BN * KC * 2 / (PAIR ? 2 : 1);
+  constexpr int MAX_A = 4, MAX_B = 8;
+  constexpr int TMEM_COLS = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int na = P.res_stages, a_stage = P.res_a_stage_bytes, nb = P.grp_b_stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + na * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + nb * B_BYTES);
+  uint64_t* afull = bars;
+  uint64_t* aempty = bars + MAX_A;
+  uint64_t* bfull = bars + 2 * MAX_A;
+  uint64_t* bempty = bfull + MAX_B;
+  uint64_t* tfull = bempty + MAX_B;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_params = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int gdim = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+  __shared__ Step s_steps[4 * kMaxSteps];
+  __shared__ int s_nsteps[4];
+  {
+    const uint32_t* src = P.tables;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_steps);
+    for (int i = threadIdx.x; i < (int)(sizeof(Step) * 4 * kMaxSteps / 4); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 4) s_nsteps[threadIdx.x] = P.nsteps[threadIdx.x];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < na; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < nb; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 16 : 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      const uint32_t afull_leader = PAIR ? mapa_u32(smem_u32(afull), 0) : 0;
+      const uint32_t bfull_leader = PAIR ? mapa_u32(smem_u32(bfull), 0) : 0;
+      const bool lead = !PAIR || crank == 0;
+      const uint32_t mult = PAIR ? 2u : 1u;
+      const int cout_pad = P.cout_pad;
+      int32_t* const perr = P.error_flag;
+      TileIter it;
+      it.init(P, bid, gdim);
+      for (int tile = bid; tile < P.tiles_total; tile += gdim, it.next(P)) {
+        const int phase = it.phase, bt = it.bt;
+        const int x0 = (PAIR ? 2 * it.xt + crank : it.xt) * P.TW, y0 = it.yt * P.TH;
+        const int brow0 = P.wkb_phase0[phase] * cout_pad + it.nt * BN + (PAIR ? crank * (BN / 2) : 0);
+        const int ns = s_nsteps[phase];
+        for (int i = 0; i < ns; ++i) {
+          const Step& sp = s_steps[phase * kMaxSteps + i];
+          const int nch = sp.nch, ntap = sp.ntap;
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&aempty[as], aph ^ 1, perr);
+            if (lead) mbar_expect_tx(&afull[as], mult * sp.bytes);
+            void* da = smem_a + as * a_stage;
+            if constexpr (PAIR) {
+              if (sp.mode == 0)
+                tma2_load_4d(da, &P.tmA[sp.src], afull_leader + 8 * as, sp.c0 + ch * KC, x0 + sp.ox, y0 + sp.oy, bt);
+              else
+                tma2_load_5d(da, &P.tmA[sp.src], afull_leader + 8 * as, sp.c0 + ch * KC, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
+            } else {
+              if (sp.mode == 0)
+                tma_load_4d(da, &P.tmA[sp.src], &afull[as], sp.c0 + ch * KC, x0 + sp.ox, y0 + sp.oy, bt);
+              else
+                tma_load_5d(da, &P.tmA[sp.src], &afull[as], sp.c0 + ch * KC, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
+            }
+            if (++as == (uint32_t)na) { as = 0; aph ^= 1; }
+            for (int t = 0; t < ntap; ++t) {
+              mbar_wait(&bempty[bs], bph ^ 1, perr);
+              if (lead) mbar_expect_tx(&bfull[bs], mult * (uint32_t)B_BYTES);
+              const int row = brow0 + ((int)(sp.tap[t] >> 16) + ch) * cout_pad;
+              if constexpr (PAIR) tma2_load_2d(smem_b + bs * B_BYTES, &P.tmB, bfull_leader + 8 * bs, 0, row);
+              else tma_load_2d(smem_b + bs * B_BYTES, &P.tmB, &bfull[bs], 0, row);
+              if (++bs == (uint32_t)nb) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (PAIR: leader CTA only)
+    if ((!PAIR || crank == 0) && elect_one()) {
+      constexpr uint32_t idesc = instr_desc<BN, PAIR ? 256 : 128>();
+      constexpr int NK = KC / 16;
+      const uint64_t desc_hi_lo = make_smem_desc<KC>(0);
+      const uint32_t a_base = smem_u32(smem_a) & 0x3FFFF, b_base = smem_u32(smem_b) & 0x3FFFF;
+      const uint32_t desc_hi_fixed = (uint32_t)(desc_hi_lo >> 32) & ~0x3fffu;
+      const uint32_t b_hi = (uint32_t)(desc_hi_lo >> 32);
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, acs = 0, acph = 0;
+      const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
+      int32_t* const perr = P.error_flag;
+      TileIter it;
+      it.init(P, bid, gdim);
+      for (int tile = bid; tile < total; tile += gdim, it.next(tn, tX, tY, tB)) {
+        const int phase = it.phase;
+        const int ns = s_nsteps[phase];
+        mbar_wait(&tempty[acs], acph ^ 1, perr);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acs * (MT * BN);
+        uint32_t acc = 0;
+        for (int i = 0; i < ns; ++i) {
+          const Step& sp = s_steps[phase * kMaxSteps + i];
+          const int nch = sp.nch, ntap = sp.ntap;
+          const uint32_t a_hi = (sp.a_sbo16 & 0x3fffu) | desc_hi_fixed;
+          const uint32_t mt_off = sp.mt_off16;
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&afull[as], aph, perr);
+            tc_fence_after();
+            const uint32_t sa_lo = ((a_base + as * a_stage) >> 4) | 0x10000u;
+            for (int t = 0; t < ntap; ++t) {
+              const uint32_t a_lo = sa_lo + (sp.tap[t] & 0xffffu);
+              const uint32_t b_lo = ((b_base + bs * B_BYTES) >> 4) | 0x10000u;
+              mbar_wait(&bfull[bs], bph, perr);
+              tc_fence_after();
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                  const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + mt * mt_off + 2 * k);
+                  const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + 2 * k);
+                  if constexpr (PAIR) umma2_bf16(d_tmem + mt * BN, ad, bd, idesc, acc | (uint32_t)k);
+                  else umma_bf16(d_tmem + mt * BN, ad, bd, idesc, acc | (uint32_t)k);
+                }
+              }
+              acc = 1;
+              if constexpr (PAIR) umma2_commit(&bempty[bs]); else umma_commit(&bempty[bs]);
+              if (++bs == (uint32_t)nb) { bs = 0; bph ^= 1; }
+            }
+            if constexpr (PAIR) umma2_commit(&aempty[as]); else umma_commit(&aempty[as]);
+            if (++as == (uint32_t)na) { as = 0; aph ^= 1; }
+          }
+        }
+        if constexpr (PAIR) umma2_commit(&tfull[acs]); else umma_commit(&tfull[acs]);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    epilogue_role<BN, MT, PAIR>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host plan
 struct Plan {
   bool ok = false;
@@ -834,6 +1132,10 @@ struct Plan {
   // tile shape (phase grid): TW*TH*NB == 128
   int Hg = 0, Wg = 0, TW = 0, TH = 0, NB = 0;
   int MT = 1;                        // 128-pixel sub-tiles per CTA tile (streaming kernel)
+  bool pair = false;                 // streaming kernel as CTA pairs (cta_group::2, M = 256, weight tile split in halves)
+  bool grouped = false;              // grouped streaming kernel (activation boxes with halo rows shared by several taps)
+  int grp_b_stages = 0, grp_smem_bytes = 0;
+  bool grp_failed = false;           // the grouped plan did not fit: re-plan without it
   // resident-weight variant
   bool resident = false;
   Step steps[4][kMaxSteps];
@@ -849,12 +1151,16 @@ int pow2_ceil_(int v) { int p = 1; while (p < v) p *= 2; return p; }
 bool g_allow_resident = true;
 bool g_allow_mt2 = true;
 bool g_allow_dual = true;
+bool g_allow_pair = true;
+bool g_allow_grp = true;
+int g_grp_halo = 1;                  // 1: grouped streaming kernel uses 8-pixel-wide tiles with a full (x and y) halo box
+int g_pair_min_kb = 16;              // short-K tiles are epilogue-paced: pairing only adds cross-CTA handshakes (measured)
 int g_halo_mode = 1;                 // 0 off, 1 halo tiles (descriptor base_offset 0: the hardware swizzle is a function of
                                      // the absolute smem address -- verified on B200), 2 = experiment: base_offset from addr bits (wrong)
 
 int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
 
-Plan build_plan(const disco_conv_desc* d) {
+Plan build_plan_impl(const disco_conv_desc* d, bool allow_grp) {
   Plan p;
   if (d->dtype != DISCO_BF16) return p;
   if (d->n_src < 1 || d->n_src > 2) return p;
@@ -950,15 +1256,36 @@ Plan build_plan(const disco_conv_desc* d) {
   int max_kb = 0;
   for (int ph = 0; ph < p.n_phase; ++ph) max_kb = p.kblocks[ph] > max_kb ? p.kblocks[ph] : max_kb;
   const int b_bytes = max_kb * p.BN * kc * 2;
-  if (!g_allow_resident || p.cout_pad != p.BN || p.BN > 64 || p.NB != 1 || TW < 8 || b_bytes > 112 * 1024) {
+  const bool want_res = g_allow_resident && p.cout_pad == p.BN && p.BN <= 64 && p.NB == 1 && TW >= 8 && b_bytes <= 112 * 1024;
+  bool halo = false;
+  if (!want_res) {
     // streaming kernel: 256-pixel tiles for narrow N when a tile stays inside one image
+    const int th_base = TH;
     if (g_allow_mt2 && p.BN <= 128 && p.NB == 1 && TW * TH == 128 && p.Hg >= 2 * TH) { p.MT = 2; p.TH = 2 * TH; }
-    return p;
-  }
+    // CTA pairs: two horizontally adjacent pixel tiles share one weight tile (wide N only: that is where the weight
+    // fill and the B-operand reads matter); needs an even number of tile columns
+    const int tiles_x = (p.Wg + p.TW - 1) / p.TW;
+    int min_kb = 1 << 30;
+    for (int ph = 0; ph < p.n_phase; ++ph) min_kb = p.kblocks[ph] < min_kb ? p.kblocks[ph] : min_kb;
+    const bool wide = (p.BN == 256 && p.MT == 1) || (p.BN == 128 && p.MT == 2);
+    p.pair = g_allow_pair && kc == 64 && tiles_x % 2 == 0 && min_kb >= g_pair_min_kb && wide;
+    // grouped variant: wide N, whole tiles inside one image, at least one tap family that can share a box
+    bool any_mode0 = false;
+    for (int ph = 0; ph < p.n_phase; ++ph)
+      for (int t = 0; t < p.ntaps[ph]; ++t) any_mode0 |= p.taps[ph][t].mode == 0;
+    const bool want_grp = g_allow_grp && allow_grp && kc == 64 && wide && p.NB == 1 && TW == 16 && th_base == 8 && p.Wg % 16 == 0 &&
+                          any_mode0 && min_kb >= g_pair_min_kb;
+    if (!want_grp) return p;
+    halo = g_grp_halo != 0 && p.Hg >= 16 * p.MT;
+    if (halo) { TW = 8; TH = 16 * p.MT; } else { TW = 16; TH = 8 * p.MT; }
+    p.TW = TW; p.TH = TH; p.NB = 1;
+    p.pair = g_allow_pair && ((p.Wg / TW) % 2 == 0);
+    p.grouped = true;
+  } else {
   // halo mode: 8-pixel-wide tiles so that an 8-row MMA group is 8 consecutive pixels of one image row; ONE box
   // with the full (TW+2) x (TH+2) halo then serves all taps of a source (A descriptors start at arbitrary pixel
   // offsets inside the box; the swizzle phase is carried by the address / descriptor base offset)
-  bool halo = g_halo_mode != 0 && p.Wg % 8 == 0 && pow2_ceil_(p.Hg) >= 16;
+  halo = g_halo_mode != 0 && p.Wg % 8 == 0 && pow2_ceil_(p.Hg) >= 16;
   if (halo) {
     // steps per tile with column grouping vs. with halo boxes (worst phase); halo tiles are 8 pixels wide, which makes
     // the stride-2-sampled taps of skip sources (one step each in both schemes) slightly costlier, so require a real gain
@@ -984,6 +1311,7 @@ Plan build_plan(const disco_conv_desc* d) {
     halo = worst_halo * 2 <= worst_grouped;
   }
   if (halo) { TW = 8; TH = 16; p.TW = TW; p.TH = TH; p.NB = 1; }
+  }
   p.halo = halo;
   // per-source extents of the mode-0 tap offsets (box = tile + span)
   int omin_y[4][2], omin_x[4][2];
@@ -1025,16 +1353,19 @@ Plan build_plan(const disco_conv_desc* d) {
         members.push_back(t);
         used[t] = true;
       }
-      if ((int)members.size() > 9) return p;
+      if ((int)members.size() > 9) { p.grp_failed = p.grouped; return p; }
       const int oy_min = tp.mode == 0 ? omin_y[ph][tp.src] : tp.oy;
       const int ox_min = (tp.mode == 0 && halo) ? omin_x[ph][tp.src] : tp.ox;
       const int row_px = (tp.mode == 0) ? TW + p.spanx[tp.src] : TW;        // pixels per box row
-      for (int ch = 0; ch < tp.nchunks; ++ch) {
-        if (ns >= kMaxSteps) return p;
+      const int n_expand = p.grouped ? 1 : tp.nchunks;     // the grouped streaming kernel loops over chunks itself
+      for (int ch = 0; ch < n_expand; ++ch) {
+        if (ns >= kMaxSteps) { p.grp_failed = p.grouped; return p; }
         Step& st = p.steps[ph][ns++];
         memset(&st, 0, sizeof(st));
         st.src = tp.src; st.mode = tp.mode; st.ox = (int8_t)ox_min; st.oy = (int8_t)oy_min; st.py = tp.py; st.px = tp.px;
         st.ntap = (int8_t)members.size();
+        st.nch = (int8_t)(p.grouped ? tp.nchunks : 1);
+        st.mt_off16 = (uint32_t)((TH / 2) * row_px * kc * 2) >> 4;
         st.c0 = tp.c_base + ch * kc;
         st.bytes = (uint32_t)((tp.mode == 0 ? (TH + p.span[tp.src]) * row_px : TH * TW) * kc * 2);
         st.a_sbo16 = (uint32_t)(((halo && tp.mode == 0) ? row_px : 8) * kc * 2) >> 4;
@@ -1047,6 +1378,18 @@ Plan build_plan(const disco_conv_desc* d) {
       }
     }
     p.nsteps[ph] = ns;
+  }
+  if (p.grouped) {
+    const int epi_cols_g = p.MT == 1 ? p.BN / 2 : p.BN;
+    const int epi_bytes_g = 8 * (3 * epi_cols_g) * 4 + 8 * 2048;
+    const int tile_b = p.BN * kc * 2 / (p.pair ? 2 : 1);
+    const int budget = 227 * 1024 - 1024 - 256 - epi_bytes_g - 4096 /* static tables */;
+    int na = 3, nbs = (budget - na * a_stage) / tile_b;
+    if (nbs > 8) { nbs = 8; if ((budget - nbs * tile_b) / a_stage >= 4) na = 4; }
+    if (nbs < 3) { p.grp_failed = true; return p; }
+    p.res_stages = na; p.res_a_stage_bytes = a_stage; p.grp_b_stages = nbs;
+    p.grp_smem_bytes = na * a_stage + nbs * tile_b + 256 + epi_bytes_g + 1024;
+    return p;
   }
   const int epi_cols = p.BN >= 32 ? p.BN / 2 : p.BN;
   const int epi_bytes = 8 * (3 * epi_cols + (p.BN <= 64 ? 9 * epi_cols : 0)) * 4 + 8 * 2048;
@@ -1068,6 +1411,12 @@ Plan build_plan(const disco_conv_desc* d) {
   p.resident = true;
   p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_bytes;
   p.res_smem_bytes = stages * a_stage + fixed;
+  return p;
+}
+
+Plan build_plan(const disco_conv_desc* d) {
+  Plan p = build_plan_impl(d, true);
+  if (p.grp_failed) p = build_plan_impl(d, false);
   return p;
 }
 
@@ -1117,10 +1466,36 @@ int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, KC, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC, MT><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
+  conv_tc_kernel<BN, KC, MT, false><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
+  return DISCO_OK;
+}
+
+// CTA-pair variant: clusters of two CTAs (one TPC), `grid` is even
+template <int BN, int KC, int MT>
+int launch_pair_cfg(const TcParams& P, int grid, cudaStream_t st) {
+  using C = Cfg<BN, KC, MT, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DISCO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, MT, true>, P));
   return DISCO_OK;
 }
 
@@ -1133,6 +1508,41 @@ int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st)
   }
   conv_tc_res_kernel<BN, KC><<<grid, kThreadsRes, smem_bytes, st>>>(P);
   return DISCO_OK;
+}
+
+template <int BN, int KC, int MT, bool PAIR>
+int launch_grp_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_grp_kernel<BN, KC, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_bytes = smem_bytes;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DISCO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_grp_kernel<BN, KC, MT, PAIR>, P));
+  return DISCO_OK;
+}
+
+int launch_grp(const Plan& pl, const TcParams& P, int grid, cudaStream_t st) {
+  if (pl.BN == 256 && pl.MT == 1)
+    return pl.pair ? launch_grp_cfg<256, 64, 1, true>(P, grid, pl.grp_smem_bytes, st)
+                   : launch_grp_cfg<256, 64, 1, false>(P, grid, pl.grp_smem_bytes, st);
+  if (pl.BN == 128 && pl.MT == 2)
+    return pl.pair ? launch_grp_cfg<128, 64, 2, true>(P, grid, pl.grp_smem_bytes, st)
+                   : launch_grp_cfg<128, 64, 2, false>(P, grid, pl.grp_smem_bytes, st);
+  disco_set_error("conv_tc: unsupported grouped configuration BN %d MT %d", pl.BN, pl.MT);
+  return DISCO_ERR_INVALID;
 }
 
 template <int KC>
@@ -1230,6 +1640,12 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     if (du && du[0] == '0') g_allow_dual = false;
     const char* m2 = getenv("DISCO_TC_MT2");
     if (m2 && m2[0] == '0') g_allow_mt2 = false;
+    const char* pr = getenv("DISCO_TC_PAIR");
+    if (pr && pr[0] == '0') g_allow_pair = false;
+    if (getenv("DISCO_TC_PAIR_MIN_KB")) g_pair_min_kb = atoi(getenv("DISCO_TC_PAIR_MIN_KB"));
+    const char* gr = getenv("DISCO_TC_GRP");
+    if (gr && gr[0] == '0') g_allow_grp = false;
+    if (getenv("DISCO_TC_GRP_HALO")) g_grp_halo = atoi(getenv("DISCO_TC_GRP_HALO"));
     const char* hm = getenv("DISCO_TC_HALO");
     if (hm) g_halo_mode = atoi(hm);
     env_read = true;
@@ -1280,9 +1696,11 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     memcpy(P.wkb_phase0, pl.wkb_phase0, sizeof(P.wkb_phase0));
     P.res_stages = pl.res_stages; P.res_a_stage_bytes = pl.res_a_stage_bytes; P.res_b_bytes = pl.res_b_bytes;
     P.res_dual = pl.res_dual ? 1 : 0;
+    P.grp_b_stages = pl.grp_b_stages;
     P.halo_bo_mask = (pl.halo && g_halo_mode == 2) ? (pl.KC == 64 ? 7 : (pl.KC == 32 ? 3 : 1)) : 0;
     P.TW = TW; P.TH = TH; P.NB = NB; P.tw_log2 = ilog2(TW); P.th_log2 = ilog2(TH);
     P.tiles_x = (P.Wg + TW - 1) / TW; P.tiles_y = (P.Hg + TH - 1) / TH; P.tiles_b = (P.B + NB - 1) / NB;
+    if (pl.pair) P.tiles_x /= 2;      // the kernel iterates over PAIRS of tile columns
     P.tiles_n = pl.cout_pad / pl.BN;
     P.tiles_total = P.tiles_x * P.tiles_y * P.tiles_b * P.tiles_n * pl.n_phase;
     P.cout_pad = pl.cout_pad;
@@ -1310,8 +1728,9 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
       if (mode == 0) {
         cuuint64_t dims[4] = {Cc, Wd, Hd, Bd};
         cuuint64_t str[3] = {Cc * 2, Wd * Cc * 2, Hd * Wd * Cc * 2};
-        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)(pl.resident ? TW + pl.spanx[s] : TW),
-                             (cuuint32_t)(pl.resident ? TH + pl.span[s] : TH), (cuuint32_t)NB};
+        const bool boxed = pl.resident || pl.grouped;
+        cuuint32_t box[4] = {(cuuint32_t)pl.KC, (cuuint32_t)(boxed ? TW + pl.spanx[s] : TW),
+                             (cuuint32_t)(boxed ? TH + pl.span[s] : TH), (cuuint32_t)NB};
         rc = encode(h, &P.tmA[s], const_cast<void*>(src.ptr), 4, dims, str, box, pl.KC);
       } else {
         DISCO_CHECK_ARG(src.H % 2 == 0 && src.W % 2 == 0, "conv_tc: stride-2 source must have even H, W");
@@ -1325,11 +1744,12 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     {
       cuuint64_t dims[2] = {(cuuint64_t)pl.KC, (cuuint64_t)pl.nkb_total * pl.cout_pad};
       cuuint64_t str[1] = {(cuuint64_t)pl.KC * 2};
-      cuuint32_t box[2] = {(cuuint32_t)pl.KC, (cuuint32_t)pl.BN};
+      cuuint32_t box[2] = {(cuuint32_t)pl.KC, (cuuint32_t)(pl.pair ? pl.BN / 2 : pl.BN)};
       int rc = encode(h, &P.tmB, const_cast<void*>(d->weights), 2, dims, str, box, pl.KC);
       if (rc != DISCO_OK) return rc;
     }
     c.grid = P.tiles_total < h->sm_count ? P.tiles_total : h->sm_count;
+    if (pl.pair) c.grid = 2 * (P.tiles_total < h->sm_count / 2 ? P.tiles_total : h->sm_count / 2);
     it = g_cache.emplace(key, c).first;
   }
   const Cached& c = it->second;
@@ -1341,6 +1761,11 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
       case 16: rc = launch_res_bn<16>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
       default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
     }
+  } else if (c.plan.grouped) {
+    rc = launch_grp(c.plan, c.params, c.grid, st);
+  } else if (c.plan.pair) {
+    if (c.plan.BN == 256) rc = launch_pair_cfg<256, 64, 1>(c.params, c.grid, st);
+    else rc = launch_pair_cfg<128, 64, 2>(c.params, c.grid, st);
   } else {
     switch (c.plan.KC) {
       case 64: rc = launch_bn<64>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;

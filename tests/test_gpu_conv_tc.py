@@ -89,6 +89,9 @@ PLAIN = [
     (64, 128, 1, 64, 32, 2), (16, 16, 1, 64, 64, 1), (16, 32, 2, 32, 32, 2), (32, 32, 1, 32, 32, 1),
     (32, 64, 1, 32, 64, 2), (256, 256, 3, 4, 4, 1), (128, 256, 5, 8, 8, 2), (64, 64, 1, 40, 24, 1),
     (256, 256, 1, 30, 40, 1), (64, 48, 1, 16, 16, 1),
+    # CTA-pair (cta_group::2) variant: wide N, even number of tile columns; ragged rows; stride 2; 256-pixel sub-tiles
+    (256, 256, 2, 16, 64, 1), (128, 256, 1, 32, 64, 2), (128, 128, 2, 64, 64, 1), (64, 128, 1, 64, 64, 2),
+    (256, 256, 1, 20, 32, 1), (512, 512, 1, 8, 96, 1), (128, 128, 3, 40, 32, 1),
 ]
 
 
@@ -107,7 +110,8 @@ def test_tc_conv3_plain_and_strided(case):
     _check(out, ref)
 
 
-@pytest.mark.parametrize("case", [(128, 64, 2, 16, 16), (512, 256, 1, 8, 16), (32, 16, 1, 32, 32), (256, 128, 2, 4, 4)], ids=str)
+@pytest.mark.parametrize("case", [(128, 64, 2, 16, 16), (512, 256, 1, 8, 16), (32, 16, 1, 32, 32), (256, 128, 2, 4, 4),
+                                  (256, 128, 1, 32, 32), (512, 256, 1, 16, 32)], ids=str)
 def test_tc_upsample_conv_parity_phases(case):
     from disentangledcolorization_b200 import _lib
     cin, cout, B, H, W = case
@@ -131,6 +135,20 @@ def test_tc_two_sources_up2_plus_direct_with_residual():
     res = _bf(torch.randn(2, 64, 16, 16, generator=g))
     ref = F.relu(F.conv2d(F.interpolate(a, scale_factor=2, mode="nearest"), wa, None, padding=1) + F.conv2d(s, ws, b, padding=1) + res)
     out = _run_tc(_lib.CONV3, 1, [(a, 1, False), (s, 0, False)], [wa, ws], b, 64, 16, 16, act=_lib.ACT_RELU, res=res)
+    _check(out, ref, ulps=3.0)
+
+
+def test_tc_two_sources_wide_pair_variant():
+    """HourGlass2 up2.combine shape family (Cout = 128): CTA-pair kernel with parity phases + stride-2-sampled skip."""
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(21)
+    a, s = _bf(torch.randn(2, 256, 16, 32, generator=g)), _bf(torch.randn(2, 128, 32, 64, generator=g))
+    wa = _bf(torch.randn(128, 256, 3, 3, generator=g) / (256 * 9) ** 0.5)
+    ws = _bf(torch.randn(128, 128, 3, 3, generator=g) / (128 * 9) ** 0.5)
+    b = torch.randn(128, generator=g) * 0.1
+    res = _bf(torch.randn(2, 128, 32, 64, generator=g))
+    ref = F.relu(F.conv2d(F.interpolate(a, scale_factor=2, mode="nearest"), wa, None, padding=1) + F.conv2d(s, ws, b, padding=1) + res)
+    out = _run_tc(_lib.CONV3, 1, [(a, 1, False), (s, 0, False)], [wa, ws], b, 128, 32, 64, act=_lib.ACT_RELU, res=res)
     _check(out, ref, ulps=3.0)
 
 
