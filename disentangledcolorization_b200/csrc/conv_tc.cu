@@ -97,6 +97,7 @@ struct TcParams {
   const float* gray;
   const float* gray_w;        // [9][Cout]
   int32_t* error_flag;
+  int32_t direct_store;       // 1: epilogue lanes store their 64-byte channel run with two 32-byte stores (no smem staging)
   int32_t dbg_mode;           // experiments: 1 = epilogue skips TMEM loads + stores, 2 = skips stores only, 3 = producer loads once
   long long* dbg;             // optional timeline buffer (DISCO_TC_DEBUG=1): [role][tile][slot] clock64 stamps of CTA 0
 };
@@ -212,6 +213,12 @@ __device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
+}
+// 32-byte (one full sector) global store
+__device__ __forceinline__ void stg256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
 }
 __device__ __forceinline__ float lds32(uint32_t saddr) {
   float v;
@@ -364,7 +371,7 @@ struct TileIter {
 // Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
 // lane quarter (w & 3) (a hardware restriction) and, when BN >= 32, the column half ((w - 2) >> 2): two warps per
 // SM sub-partition keep the epilogue's issue rate up (one warp alone runs at IPC ~0.2 on dependent fp32 math).
-template <int BN, int MT = 1, bool PAIR = false>
+template <int BN, int MT = 1, bool PAIR = false, int NACC = 2>
 __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                               float* epi_params, int warp, int lane) {
   // PAIR: this CTA owns pixel-tile column 2*xt + rank of the cluster's tile pair; accumulator-free signals go to the
@@ -394,6 +401,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   const int pCout = P.Cout, pact = P.act, phead = P.head, ptotal = P.tiles_total;
   const float pslope = P.slope;
   const bool has_post = P.post_scale != nullptr;
+  const bool pdirect = P.direct_store != 0;
   const __nv_bfloat16* const pres = P.residual;
   __nv_bfloat16* const pout = reinterpret_cast<__nv_bfloat16*>(P.out);
   int32_t* const perr = P.error_flag;
@@ -449,7 +457,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 1);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (MT * BN) + sub * BN;
     if (phead == DISCO_HEAD_NONE) {
-      if (active && P.dbg_mode != 1) {
+      if (active && P.dbg_mode != 1 && P.dbg_mode != 5) {
 #pragma unroll 1
         for (int c0 = col0; c0 < col0 + COLS; c0 += CH) {
           uint32_t r[CH];
@@ -516,6 +524,20 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
                 }
                 op[u] = make_uint4(w[0], w[1], w[2], w[3]);
               }
+            } else if (pdirect) {
+              // the shared-memory port is what bounds narrow-N tiles (operand reads of the MMAs): keep the epilogue off it.
+              // Each lane owns 64 contiguous bytes of its pixel = two full 32-byte sectors.
+              uint32_t w[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              if (P.dbg_mode != 2) {
+                __nv_bfloat16* op = pout + pix * pCout + n0 + c0;
+                stg256(op, w);
+                stg256(op + 16, w + 8);
+              }
             } else {
               // stage this lane's 64 B (32 channels) in the warp's patch, XOR-swizzled on the 16-byte piece index
 #pragma unroll
@@ -530,7 +552,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
               }
             }
           }
-          if constexpr (CH == 32) {
+          if (CH == 32 && !pdirect) {
             // coalesced write-out: 4 lanes cover one pixel's 64 B, a warp instruction writes 8 pixels x 64 B
             __syncwarp();
             const bool chunk_ok = n0 + c0 < pCout;
@@ -576,7 +598,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
       else mbar_arrive(&tempty[as]);
     }
     if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 2);
-    if (++as == 2) { as = 0; aph ^= 1; }
+    if (++as == NACC) { as = 0; aph ^= 1; }
   }
 }
 
@@ -767,13 +789,16 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P.res_b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_ST;
+  // four accumulator stages (narrow tiles leave tensor memory mostly empty): the MMA issuers run up to three tiles
+  // ahead of the epilogue, so its latency (TMEM load, math, stores) never stalls the tensor pipe
+  constexpr int NACC = 4;
   uint64_t* tfull = bars + 2 * MAX_ST;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* bfull = tempty + 2;
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* bfull = tempty + NACC;
   uint64_t* bempty = bfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + 1);
   float* epi_params = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   // step tables in shared memory: indexed reads of the multi-KB kernel-parameter block go through the constant
   // cache and cost ~60+ dependent cycles per tap inside the single-thread issue loops
   __shared__ Step s_steps[4 * kMaxSteps];
@@ -788,7 +813,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     mbar_init(bfull, 1);
     mbar_init(bempty, P.res_dual ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -827,9 +852,11 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
         for (int i = 0; i < ns; ++i) {
           const Step& sp = s_steps[phase * kMaxSteps + i];
           mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
-          mbar_expect_tx(&full[stage], sp.bytes);
+          const bool skip_a = P.dbg_mode == 3 || P.dbg_mode == 5;     // experiment: activation fill switched off
+          mbar_expect_tx(&full[stage], skip_a ? 0u : sp.bytes);
           void* da = smem_a + stage * a_stage;
-          if (sp.mode == 0)
+          if (skip_a) {
+          } else if (sp.mode == 0)
             tma_load_4d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, y0 + sp.oy, bt);
           else
             tma_load_5d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
@@ -840,7 +867,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
     }
   } else if (warp == 1 || warp == 10) {
     // ===================================================================== MMA issuers (two, alternating tiles)
-    // Issuer r owns the CTA's tiles with local index parity r (= TMEM accumulator stage r).  While one issuer sits in
+    // Issuer r owns the CTA's tiles with local index parity r (TMEM accumulator stage = local index mod NACC).  While one issuer sits in
     // its mbarrier waits / loop bookkeeping (~1000 cycles per tile, comparable to the 1700-cycle MMA batch of an
     // N = 64 tile) the other one's MMAs keep the tensor pipe busy.
     const int r = warp == 1 ? 0 : 1;
@@ -855,7 +882,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
       const uint32_t desc_hi_fixed = (uint32_t)(desc_hi_lo >> 32) & ~0x3fffu;   // version + swizzle mode
       const uint32_t b_hi = (uint32_t)(desc_hi_lo >> 32);
       const uint32_t b_lo0 = (b_base >> 4) | 0x10000u;
-      uint32_t stage = 0, ph = 0, aph = 0, bfph = 0;
+      uint32_t stage = 0, ph = 0, bfph = 0;
       int cur_phase = -1;
       const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
       int32_t* const perr = P.error_flag;
@@ -872,10 +899,9 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
           cur_phase = phase;
         }
         if (mine) {
-          const int as = dual ? r : (li & 1);
-          const uint32_t apar = dual ? aph : (uint32_t)((li >> 1) & 1);
+          const int as = li & (NACC - 1);
+          const uint32_t apar = (uint32_t)((li / NACC) & 1);
           mbar_wait(&tempty[as], apar ^ 1, perr);
-          aph ^= 1;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BN;
           uint32_t acc = 0;
@@ -917,7 +943,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
       }
     }
   } else if (warp < 10) {
-    epilogue_role<BN>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+    epilogue_role<BN, 1, false, NACC>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
@@ -1153,6 +1179,8 @@ bool g_allow_mt2 = true;
 bool g_allow_dual = true;
 bool g_allow_pair = true;
 bool g_allow_grp = true;
+int g_direct_default = 1;
+bool g_grp_mixed = false;             // group layers that mix shareable (mode 0) and stride-2-sampled (mode 1) taps
 int g_grp_halo = 1;                  // 1: grouped streaming kernel uses 8-pixel-wide tiles with a full (x and y) halo box
 int g_pair_min_kb = 16;              // short-K tiles are epilogue-paced: pairing only adds cross-CTA handshakes (measured)
 int g_halo_mode = 1;                 // 0 off, 1 halo tiles (descriptor base_offset 0: the hardware swizzle is a function of
@@ -1276,7 +1304,12 @@ Plan build_plan_impl(const disco_conv_desc* d, bool allow_grp) {
     const bool want_grp = g_allow_grp && allow_grp && kc == 64 && wide && p.NB == 1 && TW == 16 && th_base == 8 && p.Wg % 16 == 0 &&
                           any_mode0 && min_kb >= g_pair_min_kb;
     if (!want_grp) return p;
-    halo = g_grp_halo != 0 && p.Hg >= 16 * p.MT;
+    bool any_mode1 = false;
+    for (int ph = 0; ph < p.n_phase; ++ph)
+      for (int t = 0; t < p.ntaps[ph]; ++t) any_mode1 |= p.taps[ph][t].mode == 1;
+    if (any_mode1 && !g_grp_mixed) return p;
+    // 8-pixel-wide halo tiles make the stride-2-sampled boxes of skip sources costlier (measured): row halo only there
+    halo = g_grp_halo != 0 && p.Hg >= 16 * p.MT && !any_mode1;
     if (halo) { TW = 8; TH = 16 * p.MT; } else { TW = 16; TH = 8 * p.MT; }
     p.TW = TW; p.TH = TH; p.NB = 1;
     p.pair = g_allow_pair && ((p.Wg / TW) % 2 == 0);
@@ -1646,6 +1679,7 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     const char* gr = getenv("DISCO_TC_GRP");
     if (gr && gr[0] == '0') g_allow_grp = false;
     if (getenv("DISCO_TC_GRP_HALO")) g_grp_halo = atoi(getenv("DISCO_TC_GRP_HALO"));
+    if (getenv("DISCO_TC_GRP_MIXED")) g_grp_mixed = atoi(getenv("DISCO_TC_GRP_MIXED")) != 0;
     const char* hm = getenv("DISCO_TC_HALO");
     if (hm) g_halo_mode = atoi(hm);
     env_read = true;
@@ -1672,6 +1706,11 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     }
     P.error_flag = g_error_flag;
     if (getenv("DISCO_TC_MODE")) P.dbg_mode = atoi(getenv("DISCO_TC_MODE"));
+    {
+      // bit 0: resident kernel, bit 1: streaming kernels
+      const int dm = getenv("DISCO_TC_DIRECT") ? atoi(getenv("DISCO_TC_DIRECT")) : g_direct_default;
+      P.direct_store = (pl.resident ? (dm & 1) : (dm & 2)) ? 1 : 0;
+    }
     if (getenv("DISCO_TC_DEBUG")) {
       if (!g_dbg) {
         DISCO_CUDA(cudaMalloc(&g_dbg, sizeof(long long) * 4 * kDbgTiles * kDbgSlots));
