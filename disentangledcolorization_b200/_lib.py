@@ -31,7 +31,9 @@ class ConvDesc(C.Structure):
                 ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32), ("n_src", C.c_int32),
                 ("src", ConvSrc * 2), ("weights", C.c_void_p), ("bias", C.c_void_p), ("post_scale", C.c_void_p),
                 ("post_shift", C.c_void_p), ("residual", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float),
-                ("head", C.c_int32), ("out", C.c_void_p), ("gray_weights", C.c_void_p)]
+                ("head", C.c_int32), ("out", C.c_void_p), ("gray_weights", C.c_void_p),
+                ("bias_host", C.c_void_p), ("post_scale_host", C.c_void_p), ("post_shift_host", C.c_void_p),
+                ("gray_weights_host", C.c_void_p)]
 
 
 class LinearDesc(C.Structure):

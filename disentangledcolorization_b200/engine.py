@@ -64,6 +64,10 @@ class _PackedConv:
         self.w16 = None        # tensor-core (bf16) packing, filled on first use
         self.w_off = offs
         self.bias = folded.bias.to(device)
+        # host copies: narrow tensor-core layers take their epilogue parameters through the kernel-parameter block
+        self.bias_host = folded.bias.detach().float().contiguous().cpu()
+        self.post_scale_host = folded.post_scale.detach().float().contiguous().cpu() if folded.post_scale is not None else None
+        self.post_shift_host = folded.post_shift.detach().float().contiguous().cpu() if folded.post_shift is not None else None
         self.post_scale = folded.post_scale.to(device) if folded.post_scale is not None else None
         self.post_shift = folded.post_shift.to(device) if folded.post_shift is not None else None
 
@@ -224,6 +228,9 @@ class Engine:
         d.weights, d.bias = pc.w32.data_ptr(), pc.bias.data_ptr()
         d.post_scale = pc.post_scale.data_ptr() if pc.post_scale is not None else None
         d.post_shift = pc.post_shift.data_ptr() if pc.post_shift is not None else None
+        d.bias_host = pc.bias_host.data_ptr()
+        d.post_scale_host = pc.post_scale_host.data_ptr() if pc.post_scale_host is not None else None
+        d.post_shift_host = pc.post_shift_host.data_ptr() if pc.post_shift_host is not None else None
         d.residual = bufs[op.res].data_ptr() if op.res else None
         d.act, d.slope, d.head = _ACT[op.act], op.slope, _HEAD[op.head]
         d.out = bufs[op.out].data_ptr()
@@ -244,6 +251,7 @@ class Engine:
         for i in range(d.n_src):
             if d.src[i].is_f32:
                 d.gray_weights = pc.w32.data_ptr() + 4 * int(d.src[i].w_off)
+                d.gray_weights_host = pc.w32_host.data_ptr() + 4 * int(d.src[i].w_off)
         return True
 
     def _run_net(self, net, ws, B, gray, stream):

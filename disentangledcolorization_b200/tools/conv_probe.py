@@ -38,6 +38,13 @@ def build_desc(handle, cin, cout, B, H, W, stride=1, up2=0, head=0, act=1, post=
         d.residual = r.data_ptr()
         keep.update(r=r)
     d.act, d.slope, d.head = act, 0.2, head
+    bh = bias.cpu().contiguous()
+    d.bias_host = bh.data_ptr()
+    keep.update(bh=bh)
+    if post:
+        psh, pbh = keep["ps"].cpu().contiguous(), keep["pb"].cpu().contiguous()
+        d.post_scale_host, d.post_shift_host = psh.data_ptr(), pbh.data_ptr()
+        keep.update(psh=psh, pbh=pbh)
     out = (torch.empty(B, cout, Ho, Wo, device="cuda") if head else
            torch.empty(B, Ho, Wo, cout, device="cuda", dtype=torch.bfloat16))
     d.out = out.data_ptr()

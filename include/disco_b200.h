@@ -92,6 +92,13 @@ typedef struct {
   int32_t head;             /* disco_head */
   void* out;                /* NHWC (dtype) or, with a head, fp32 NCHW */
   const float* gray_weights; /* tensor-core path only: fp32 [9][Cout] weights of the fp32 1-channel source */
+  /* Optional HOST copies of bias / post_scale / post_shift / gray_weights (same values as the device arrays; NULL = not
+   * supplied).  When present, narrow (Cout <= 64) tensor-core layers pass them in the kernel-parameter block so the
+   * epilogue reads them as constant-bank operands instead of through shared memory.  Read at every disco_conv call. */
+  const float* bias_host;
+  const float* post_scale_host;
+  const float* post_shift_host;
+  const float* gray_weights_host;
 } disco_conv_desc;
 
 int disco_conv(disco_handle* h, const disco_conv_desc* d, void* stream);

@@ -23,8 +23,10 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
 
-def _run_tc(kind, stride, srcs, weights, bias, cout, Ho, Wo, act=0, slope=0.0, post=None, res=None, head=0, expect_tc=True):
-    """srcs: list of (NCHW fp32 tensor, up2, is_gray)."""
+def _run_tc(kind, stride, srcs, weights, bias, cout, Ho, Wo, act=0, slope=0.0, post=None, res=None, head=0, expect_tc=True,
+            host_params=True):
+    """srcs: list of (NCHW fp32 tensor, up2, is_gray).  host_params: also pass the optional host copies of the epilogue
+    parameters (narrow layers then read them from the constant bank)."""
     from disentangledcolorization_b200 import _lib
     h = _lib.Handle.get(0)
     B = srcs[0][0].shape[0]
@@ -56,6 +58,14 @@ def _run_tc(kind, stride, srcs, weights, bias, cout, Ho, Wo, act=0, slope=0.0, p
         keep.append(r)
         d.residual = r.data_ptr()
     d.act, d.slope, d.head = act, slope, head
+    if host_params:
+        bh = bias.float().contiguous()
+        keep.append(bh)
+        d.bias_host = bh.data_ptr()
+        if post is not None:
+            psh, pbh = post[0].float().contiguous(), post[1].float().contiguous()
+            keep += [psh, pbh]
+            d.post_scale_host, d.post_shift_host = psh.data_ptr(), pbh.data_ptr()
     out = torch.empty(B, cout, Ho, Wo, device="cuda") if head else torch.empty(B, Ho, Wo, cout, device="cuda", dtype=torch.bfloat16)
     d.out = out.data_ptr()
     d.weights = w32_dev.data_ptr()
@@ -70,6 +80,8 @@ def _run_tc(kind, stride, srcs, weights, bias, cout, Ho, Wo, act=0, slope=0.0, p
         for i in range(d.n_src):
             if d.src[i].is_f32:
                 d.gray_weights = w32_dev.data_ptr() + 4 * offs[i]
+                if host_params:
+                    d.gray_weights_host = w32_host.data_ptr() + 4 * offs[i]
     _lib.check(h.lib.disco_conv(h.h, C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "disco_conv")
     torch.cuda.synchronize()
     o = out.float().cpu()
@@ -195,6 +207,22 @@ def test_tc_heads_and_gray_side_input():
     ref = F.relu(F.conv2d(torch.cat((gray, x64), 1), w65, b, padding=1))
     out = _run_tc(_lib.CONV3, 1, [(gray, 0, True), (x64, 0, False)], [w65[:, :1], w65[:, 1:]], b, 64, 32, 32, act=_lib.ACT_RELU)
     _check(out, ref)
+
+
+@pytest.mark.parametrize("cout", [16, 32, 64])
+def test_tc_narrow_layers_without_host_parameter_copies(cout):
+    """The shared-memory parameter cache path (descriptor without the optional host copies) stays correct."""
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(40 + cout)
+    x = _bf(torch.randn(2, 32, 32, 32, generator=g))
+    w = _bf(torch.randn(cout, 32, 3, 3, generator=g) / (32 * 9) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ps, pb = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.1) * ps.view(1, -1, 1, 1) + pb.view(1, -1, 1, 1)
+    for hp in (False, True):
+        out = _run_tc(_lib.CONV3, 1, [(x, 0, False)], [w], b, cout, 32, 32, act=_lib.ACT_LRELU, slope=0.1, post=(ps, pb),
+                      host_params=hp)
+        _check(out, ref)
 
 
 def test_cin1_layers_stay_on_cuda_cores():
