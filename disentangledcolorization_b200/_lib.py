@@ -14,7 +14,7 @@ ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 HEAD_NONE, HEAD_SOFTMAX9, HEAD_TANH2 = 0, 1, 2
 CONV3, DECONV4 = 0, 1
 
-EXPORTS = ["disco_version", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
+EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
            "disco_reset_launch_count", "disco_add_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",

@@ -1,5 +1,6 @@
 // C-ABI plumbing of libdisco_b200.so: handle lifetime, error reporting, conv dispatch.
 #include "common.cuh"
+#include <cstddef>
 #include <cstring>
 #include <new>
 
@@ -12,7 +13,19 @@ void disco_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-extern "C" int disco_version(void) { return 100; }
+extern "C" int disco_version(void) { return 101; }
+// ABI self-description for bindings: 0 = sizeof(disco_conv_src), 1 = sizeof(disco_conv_desc), 2 = sizeof(disco_linear_desc),
+// 3 = offsetof(disco_conv_desc, out), 4 = offsetof(disco_conv_desc, bias_host)
+extern "C" int disco_abi_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(disco_conv_src);
+    case 1: return (int)sizeof(disco_conv_desc);
+    case 2: return (int)sizeof(disco_linear_desc);
+    case 3: return (int)offsetof(disco_conv_desc, out);
+    case 4: return (int)offsetof(disco_conv_desc, bias_host);
+  }
+  return -1;
+}
 
 extern "C" const char* disco_last_error(void) { return g_err; }
 

@@ -41,6 +41,10 @@ enum disco_head { DISCO_HEAD_NONE = 0, DISCO_HEAD_SOFTMAX9 = 1, DISCO_HEAD_TANH2
 enum disco_conv_kind { DISCO_CONV3 = 0, DISCO_DECONV4 = 1 };
 
 int disco_version(void);
+/* sizes/offsets of the descriptor structs as compiled (for language bindings to verify their mirrors):
+ * 0 sizeof(disco_conv_src), 1 sizeof(disco_conv_desc), 2 sizeof(disco_linear_desc), 3 offsetof(conv_desc, out),
+ * 4 offsetof(conv_desc, bias_host) */
+int disco_abi_size(int which);
 const char* disco_last_error(void);
 int disco_create(disco_handle** out, int device);
 int disco_destroy(disco_handle* h);

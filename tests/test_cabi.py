@@ -30,9 +30,16 @@ def test_struct_layout_matches_header():
     """ctypes mirrors of the descriptor structs have the C layout (sizes from the compiler's rules)."""
     from disentangledcolorization_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSrc) == 40
-    assert ctypes.sizeof(_lib.ConvDesc) == 32 + 80 + 5 * 8 + 16 + 8 + 8
+    assert ctypes.sizeof(_lib.ConvDesc) == 32 + 80 + 5 * 8 + 16 + 8 + 8 + 4 * 8
     assert _lib.ConvDesc.src.offset == 32 and _lib.ConvDesc.out.offset == 168
     assert ctypes.sizeof(_lib.LinearDesc) == 136
+    # ... and equal what the compiler laid out (the library describes its own ABI; no GPU needed)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    assert lib.disco_abi_size(0) == ctypes.sizeof(_lib.ConvSrc)
+    assert lib.disco_abi_size(1) == ctypes.sizeof(_lib.ConvDesc)
+    assert lib.disco_abi_size(2) == ctypes.sizeof(_lib.LinearDesc)
+    assert lib.disco_abi_size(3) == _lib.ConvDesc.out.offset
+    assert lib.disco_abi_size(4) == _lib.ConvDesc.bias_host.offset
 
 
 def test_product_path_fails_loudly_without_cuda():
