@@ -378,7 +378,16 @@ struct TileIter {
 // Warps 2..9 (8 warps): TMEM -> registers -> fused math -> global.  Shared by both kernels.  Warp w reads TMEM
 // lane quarter (w & 3) (a hardware restriction) and, when BN >= 32, the column half ((w - 2) >> 2): two warps per
 // SM sub-partition keep the epilogue's issue rate up (one warp alone runs at IPC ~0.2 on dependent fp32 math).
-template <int BN, int MT = 1, bool PAIR = false, int NACC = 2, bool CP = false>
+template <class T> struct CVal { static constexpr int value = 0; };
+template <int V> struct CVal<std::integral_constant<int, V>> { static constexpr int value = V; };
+__device__ __forceinline__ int cval_rt(int v) { return v; }
+template <int V> __device__ __forceinline__ int cval_rt(std::integral_constant<int, V>) { return V; }
+
+// ALT (resident kernel): the two warps of a lane quarter take ALTERNATE tiles and all BN columns each, instead of
+// splitting the columns of every tile.  Timeline stamps showed ~2300 cycles per tile and warp for 64-channel tiles, of
+// which ~1000 are per-tile fixed cost (barrier wait, tile bookkeeping, address math): the epilogue, not the tensor pipe,
+// paced these layers.  Alternating halves the fixed cost per tile.
+template <int BN, int MT = 1, bool PAIR = false, int NACC = 2, bool CP = false, bool ALT = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                               float* epi_params, int warp, int lane) {
   // PAIR: this CTA owns pixel-tile column 2*xt + rank of the cluster's tile pair; accumulator-free signals go to the
@@ -390,18 +399,21 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
   // MT == 1: the two warps of a lane quarter split the columns.  MT == 2: they take one 128-pixel sub-tile each.
-  constexpr int NHALF = (BN >= 32 && MT == 1) ? 2 : 1;   // column halves
+  static_assert(!ALT || (MT == 1 && !PAIR), "alternating epilogue: single 128-pixel tiles only");
+  static_assert(!CP || ALT, "constant-bank parameters are used by the resident kernel only");
+  constexpr int NHALF = ALT ? 1 : ((BN >= 32 && MT == 1) ? 2 : 1);   // column halves
   constexpr int COLS = BN / NHALF;              // columns this warp owns
-  constexpr int EPI_FLOATS = 3 * COLS + (BN <= 64 ? 9 * COLS : 0);   // per-warp cache: bias|scale|shift(|9 gray taps)
+  // per-warp cache: bias|scale|shift(|9 gray taps); the resident kernel sizes it at run time (host mirrors this)
+  const int EPI_FLOATS = ALT ? (3 * COLS + (P.gray ? 9 * COLS : 0)) : (3 * COLS + (BN <= 64 ? 9 * COLS : 0));
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
-  const bool active = half < NHALF * MT;
+  const bool active = ALT ? true : half < NHALF * MT;
   const int sub = MT == 2 ? half : 0;           // 128-pixel sub-tile of this warp
   const int m = sub * 128 + q * 32 + lane;      // pixel within the tile
   const int tx = m & (P.TW - 1), ty = (m >> P.tw_log2) & (P.TH - 1), nb = m >> (P.tw_log2 + P.th_log2);
   const uint32_t wp = smem_u32(epi_params + (warp - 2) * EPI_FLOATS);   // this warp's private parameter cache
   const uint32_t stg = smem_u32(epi_params + 8 * EPI_FLOATS) + (warp - 2) * EPI_STAGE;   // output staging patch
-  const int col0 = MT == 2 ? 0 : half * COLS;
+  const int col0 = (MT == 2 || ALT) ? 0 : half * COLS;
   // hot parameters hoisted out of the tile loop (the parameter block is several KB: re-reading it through the
   // constant cache inside the loop stalls on misses)
   const int pTW = P.TW, pTH = P.TH, pNB = P.NB, pWg = P.Wg, pHg = P.Hg, pB = P.B, pos = P.os, pHo = P.Ho, pWo = P.Wo;
@@ -417,7 +429,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   TileIter it;
   it.init(P, bid, gdim);
   const int tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
-  for (int tile = bid; tile < ptotal; tile += gdim, it.next(tn, tX, tY, tB)) {
+  int li = 0;                                   // local tile index
+  for (int tile = bid; tile < ptotal; tile += gdim, it.next(tn, tX, tY, tB), ++li) {
+    if constexpr (ALT) {
+      if ((li & 1) != half) continue;           // the other warp of this lane quarter owns this tile
+      as = (uint32_t)li & (NACC - 1);
+      aph = ((uint32_t)li / NACC) & 1;
+    }
     const int phase = it.phase, nt = it.nt;
     const int X = (PAIR ? 2 * it.xt + crank : it.xt) * pTW + tx, Y = it.yt * pTH + ty, b = it.bt * pNB + nb;
     const bool valid = active && X < pWg && Y < pHg && b < pB;
@@ -466,18 +484,18 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     if (phead == DISCO_HEAD_NONE) {
       // CP: the warp's column half is a compile-time constant inside each instantiation of this lambda, so the
       // parameter reads below are constant-bank operands with immediate offsets (P.epi_c[k][HALF * COLS + j])
-      auto run_chunks = [&](auto half_tag) {
-        constexpr int HALF = decltype(half_tag)::value;
-        static_assert(!CP || (COLS == CH && BN <= 64), "constant-bank parameters: one chunk per warp, one n-tile");
-#pragma unroll 1
-        for (int c0 = col0; c0 < col0 + COLS; c0 += CH) {
+      // one accumulator chunk of CH columns starting at column c0v (a compile-time constant in CP mode, so that the
+      // parameter reads are constant-bank operands with immediate offsets)
+      auto do_chunk = [&](auto c0v) {
+        const int c0 = cval_rt(c0v);
+        {
           uint32_t r[CH];
           tmem_ld<CH>(taddr + c0, r);
           if (valid && n0 + c0 < pCout) {
             float v[CH];
             if constexpr (CP) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + P.epi_c[0][HALF * COLS + j];
+              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) + P.epi_c[0][CVal<decltype(c0v)>::value + j];
             } else {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
@@ -521,7 +539,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
             }
             if (has_post && CP) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = fmaf(v[j], P.epi_c[1][HALF * COLS + j], P.epi_c[2][HALF * COLS + j]);
+              for (int j = 0; j < CH; ++j)
+                v[j] = fmaf(v[j], P.epi_c[1][CVal<decltype(c0v)>::value + j], P.epi_c[2][CVal<decltype(c0v)>::value + j]);
             } else if (has_post) {
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
@@ -589,11 +608,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
         }
       };
       if (active && P.dbg_mode != 1 && P.dbg_mode != 5) {
-        if constexpr (CP && NHALF == 2) {
-          if (half == 0) run_chunks(std::integral_constant<int, 0>{});
-          else run_chunks(std::integral_constant<int, 1>{});
+        if constexpr (CP) {
+          static_assert(COLS <= 2 * CH, "at most two chunks per warp");
+          do_chunk(std::integral_constant<int, 0>{});
+          if constexpr (COLS > CH) do_chunk(std::integral_constant<int, CH>{});
         } else {
-          run_chunks(std::integral_constant<int, 0>{});
+#pragma unroll 1
+          for (int c0 = col0; c0 < col0 + COLS; c0 += CH) do_chunk(c0);
         }
       }
     } else if (active) {
@@ -626,7 +647,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
       else mbar_arrive(&tempty[as]);
     }
     if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, (tile - bid) / gdim, 2);
-    if (++as == NACC) { as = 0; aph ^= 1; }
+    if constexpr (!ALT) {
+      if (++as == NACC) { as = 0; aph ^= 1; }
+    }
   }
 }
 
@@ -841,7 +864,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }   // 4 warps own a tile
     mbar_init(bfull, 1);
     mbar_init(bempty, P.res_dual ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -929,14 +952,17 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
         if (mine) {
           const int as = li & (NACC - 1);
           const uint32_t apar = (uint32_t)((li / NACC) & 1);
+          dbg_stamp(P, 1, li, 0);
           mbar_wait(&tempty[as], apar ^ 1, perr);
           tc_fence_after();
+          dbg_stamp(P, 1, li, 1);
           const uint32_t d_tmem = tmem_base + as * BN;
           uint32_t acc = 0;
           for (int i = 0; i < ns; ++i) {
             const Step& sp = s_steps[phase * kMaxSteps + i];
             mbar_wait(&full[stage], ph, perr);
             tc_fence_after();
+            dbg_stamp(P, 1, li, 2 + (i < 2 ? i : 2));
             // Descriptors are assembled from 32-bit halves with one add per tap: the hi words (stride, version,
             // swizzle mode) are loop invariants, the lo word is (smem address >> 4) | LBO.
             const uint32_t sa_lo = ((a_base + stage * a_stage) >> 4) | 0x10000u;
@@ -961,6 +987,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
             if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
           }
           umma_commit(&tfull[as]);
+          dbg_stamp(P, 1, li, 6);
         } else {
           // the other issuer's tile: only track which pipeline stages it consumes
           for (int i = 0; i < ns; ++i)
@@ -971,7 +998,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
       }
     }
   } else if (warp < 10) {
-    epilogue_role<BN, 1, false, NACC, CP>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+    epilogue_role<BN, 1, false, NACC, CP, true>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
@@ -1453,8 +1480,8 @@ Plan build_plan_impl(const disco_conv_desc* d, bool allow_grp) {
     p.grp_smem_bytes = na * a_stage + nbs * tile_b + 256 + epi_bytes_g + 1024;
     return p;
   }
-  const int epi_cols = p.BN >= 32 ? p.BN / 2 : p.BN;
-  const int epi_bytes = 8 * (3 * epi_cols + (p.BN <= 64 ? 9 * epi_cols : 0)) * 4 + 8 * 2048;
+  const int epi_cols = p.BN;       // alternating epilogue: every warp owns all columns of its tiles
+  const int epi_bytes = 8 * (3 * epi_cols + (p.gray_src >= 0 ? 9 * epi_cols : 0)) * 4 + 8 * 2048;
   const int fixed = b_bytes + 256 + epi_bytes + 1024;
   int stages = (225 * 1024 - fixed) / a_stage;
   if (stages > 8) stages = 8;

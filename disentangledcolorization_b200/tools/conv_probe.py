@@ -99,10 +99,10 @@ def main():
         t = buf.reshape(4, 48, 8)
         t0 = t[t > 0].min() if (t > 0).any() else 0
         rel = np.where(t > 0, t - t0, -1)
-        names = ["producer(step issue)", "mma(0 pre-tempty,1 post,2.. full[i],7 commit)", "epi w2 (0 pre,1 got tfull,2 done)", "epi w6"]
+        names = ["producer(step issue)", "mma(0 pre-tempty,1 post,2.. full[i],6 commit)", "epi w2 (0 pre,1 got tfull,2 done)", "epi w6"]
         for r in range(4):
             print(names[r])
-            for ti in range(0, 40):
+            for ti in range(0, 24):
                 print("  tile", ti, rel[r, ti].tolist())
     print(f"cin={a.cin} cout={a.cout} hw={a.hw} B={a.batch} stride={a.stride} up2={a.up2} head={a.head} kind={a.kind} "
           f"tc={tc}: {ms:.4f} ms  {flops / ms / 1e9:.1f} TFLOP/s (reference-formulation FLOPs)")
