@@ -168,6 +168,11 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
 }
 // ---- CTA-pair (cta_group::2) variants: loads land in the executing CTA's shared memory, the transaction bytes are
 // signalled on the LEADER CTA's mbarrier (`bar_cluster` = shared::cluster address obtained with mapa)
+// Programmatic dependent launch: every tensor-core kernel is launched with programmaticStreamSerialization, so its CTAs
+// may become resident (barrier setup, tensor-memory allocation, weight loads) while the tail of the previous kernel is
+// still draining; nothing that depends on the previous kernel's output may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -396,6 +401,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int gdim = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(tempty), 0) : 0;
+  pdl_wait();                                   // residual / L-channel reads and all stores come after the previous kernel
   constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
   // MT == 1: the two warps of a lane quarter split the columns.  MT == 2: they take one 128-pixel sub-tile each.
@@ -705,10 +711,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (elect_one()) {
+      pdl_wait();
       uint32_t stage = 0, ph = 0;
       const uint32_t full_leader = PAIR ? mapa_u32(smem_u32(full), 0) : 0;
       const bool skip_a = P.dbg_mode == 3, skip_b = P.dbg_mode == 4;     // experiments: operand fill switched off
@@ -880,6 +888,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_phase = P.tiles_n * P.tiles_x * P.tiles_y * P.tiles_b;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -900,6 +909,7 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
         }
         const int x0 = it.xt * P.TW, y0 = it.yt * P.TH;
         const int ns = s_nsteps[phase];
+        if (tile == (int)blockIdx.x) pdl_wait();     // the weights above are static; activations come from the previous kernel
         for (int i = 0; i < ns; ++i) {
           const Step& sp = s_steps[phase * kMaxSteps + i];
           mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
@@ -1074,10 +1084,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_grp_kernel(const __grid_c
   if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (elect_one()) {
+      pdl_wait();
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       const uint32_t afull_leader = PAIR ? mapa_u32(smem_u32(afull), 0) : 0;
       const uint32_t bfull_leader = PAIR ? mapa_u32(smem_u32(bfull), 0) : 0;
@@ -1550,6 +1562,36 @@ std::map<std::string, Cached> g_cache;
 int32_t* g_error_flag = nullptr;
 long long* g_dbg = nullptr;
 
+bool g_allow_pdl = true;
+// Every tensor-core launch: optional 2-CTA clusters + programmatic stream serialization (see pdl_wait()).
+template <typename Kern>
+int launch_tc(Kern kern, const TcParams& P, int grid, int threads, size_t smem, int cluster, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_allow_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)na;
+  DISCO_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+  return DISCO_OK;
+}
+
 template <int BN, int KC, int MT>
 int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, KC, MT>;
@@ -1558,8 +1600,7 @@ int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
     DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KC, MT, false><<<grid, kThreads, C::SMEM_BYTES, st>>>(P);
-  return DISCO_OK;
+  return launch_tc(conv_tc_kernel<BN, KC, MT, false>, P, grid, kThreads, C::SMEM_BYTES, 1, st);
 }
 
 // CTA-pair variant: clusters of two CTAs (one TPC), `grid` is even
@@ -1571,21 +1612,7 @@ int launch_pair_cfg(const TcParams& P, int grid, cudaStream_t st) {
     DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DISCO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, MT, true>, P));
-  return DISCO_OK;
+  return launch_tc(conv_tc_kernel<BN, KC, MT, true>, P, grid, kThreads, C::SMEM_BYTES, 2, st);
 }
 
 template <int BN, int KC, bool CP>
@@ -1595,8 +1622,7 @@ int launch_res_cfg2(const TcParams& P, int grid, int smem_bytes, cudaStream_t st
     DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes = smem_bytes;
   }
-  conv_tc_res_kernel<BN, KC, CP><<<grid, kThreadsRes, smem_bytes, st>>>(P);
-  return DISCO_OK;
+  return launch_tc(conv_tc_res_kernel<BN, KC, CP>, P, grid, kThreadsRes, (size_t)smem_bytes, 1, st);
 }
 template <int BN, int KC>
 int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
@@ -1611,21 +1637,7 @@ int launch_grp_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st)
     DISCO_CUDA(cudaFuncSetAttribute(conv_tc_grp_kernel<BN, KC, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes = smem_bytes;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = (size_t)smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DISCO_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_grp_kernel<BN, KC, MT, PAIR>, P));
-  return DISCO_OK;
+  return launch_tc(conv_tc_grp_kernel<BN, KC, MT, PAIR>, P, grid, kThreads, (size_t)smem_bytes, PAIR ? 2 : 1, st);
 }
 
 int launch_grp(const Plan& pl, const TcParams& P, int grid, cudaStream_t st) {
@@ -1737,6 +1749,8 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     const char* pr = getenv("DISCO_TC_PAIR");
     if (pr && pr[0] == '0') g_allow_pair = false;
     if (getenv("DISCO_TC_PAIR_MIN_KB")) g_pair_min_kb = atoi(getenv("DISCO_TC_PAIR_MIN_KB"));
+    const char* pd = getenv("DISCO_TC_PDL");
+    if (pd && pd[0] == '0') g_allow_pdl = false;
     const char* cp = getenv("DISCO_TC_CONST");
     if (cp && cp[0] == '0') g_allow_const = false;
     const char* gr = getenv("DISCO_TC_GRP");

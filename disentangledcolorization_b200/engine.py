@@ -509,6 +509,18 @@ class Engine:
             return 2.0 * B * (Ho // 2) * (Wo // 2) * op.cin * op.cout * 16
         return 2.0 * B * Ho * Wo * op.cin * op.cout * 9
 
+    @staticmethod
+    def executed_flops(op, B, Ho, Wo):
+        """2 x MACs the kernels actually issue: a nearest-upsampled source is convolved as four 2x2-tap parity phases
+        on the low-resolution map (4/9 of the reference formulation's MACs); everything else equals algorithmic_flops."""
+        if op.kind == "deconv4":
+            return 2.0 * B * (Ho // 2) * (Wo // 2) * op.cin * op.cout * 16
+        f = 0.0
+        for s in op.srcs:
+            c = s.cin[1] - s.cin[0]
+            f += 2.0 * B * Ho * Wo * c * op.cout * (4 if s.up2 else 9)
+        return f
+
     def profile_convs(self, gray, ab, steps=2):
         """Times every disco_conv launch of `steps` forwards with CUDA events on the launching stream."""
         self.forward(gray, ab)
@@ -528,13 +540,16 @@ class Engine:
             f = self.algorithmic_flops(op, B, Ho, Wo)
             flops += f
             ms += t
-            a = per_op.setdefault(op.name, [0.0, 0.0, op.cout])
+            a = per_op.setdefault(op.name, [0.0, 0.0, op.cout, 0.0, op])
             a[0] += f
             a[1] += t
+            a[3] += self.executed_flops(op, B, Ho, Wo)
         top = sorted(per_op.items(), key=lambda kv: -kv[1][1])[:6]
         return {"flops": flops / steps, "ms": ms / steps,
                 "top": [{"op": k, "ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12} for k, v in top],
-                "per_op": {k: {"ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12, "flops": v[0] / steps, "cout": v[2]}
+                "per_op": {k: {"ms": v[1] / steps, "tflops": v[0] / (v[1] / 1e3) / 1e12, "flops": v[0] / steps, "cout": v[2],
+                               "executed_flops": v[3] / steps, "cin": v[4].cin, "stride": v[4].stride, "n_src": len(v[4].srcs),
+                               "up2": any(s.up2 for s in v[4].srcs), "kind": v[4].kind}
                            for k, v in per_op.items()}}
 
     def kmeans_iterations(self, B, H, W):
