@@ -405,7 +405,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   constexpr int EPI_STAGE = 2048;               // per-warp output staging patch: 32 pixels x 64 B
   constexpr int CH = BN >= 64 ? 32 : 16;        // accumulator columns per tcgen05.ld
   // MT == 1: the two warps of a lane quarter split the columns.  MT == 2: they take one 128-pixel sub-tile each.
-  static_assert(!ALT || (MT == 1 && !PAIR), "alternating epilogue: single 128-pixel tiles only");
+  static_assert(!ALT || MT == 1, "alternating epilogue: single 128-pixel tiles only");
   static_assert(!CP || ALT, "constant-bank parameters are used by the resident kernel only");
   constexpr int NHALF = ALT ? 1 : ((BN >= 32 && MT == 1) ? 2 : 1);   // column halves
   constexpr int COLS = BN / NHALF;              // columns this warp owns
@@ -497,6 +497,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
         {
           uint32_t r[CH];
           tmem_ld<CH>(taddr + c0, r);
+          if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, li, 3 + (c0 != col0 ? 2 : 0));
           if (valid && n0 + c0 < pCout) {
             float v[CH];
             if constexpr (CP) {
@@ -577,6 +578,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                 w[j] = *reinterpret_cast<uint32_t*>(&h2);
               }
+              if (lane == 0 && (warp == 2 || warp == 6)) dbg_stamp(P, warp == 2 ? 2 : 3, li, 4 + (c0 != col0 ? 2 : 0));
               if (P.dbg_mode != 2) {
                 __nv_bfloat16* op = pout + pix * pCout + n0 + c0;
                 stg256(op, w);
@@ -836,9 +838,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 //     and 3 instead of 9 mbarrier round trips, which is what bounds N <= 64 tiles (their MMAs are short).
 // Shared-memory layout: [stages x A stage][resident weights][barriers][epilogue parameter caches].
 // ------------------------------------------------------------------------------------------------
-template <int BN, int KC, bool CP>
+// PAIR: clusters of two CTAs on horizontally adjacent tiles run cta_group::2 MMAs (M = 256): each CTA keeps only half of
+// every weight block resident (N/2 rows) -- 5 KB instead of 6 KB of shared-memory operand reads per N = 64 MMA (the read
+// port is what paces them) -- and ONE thread issues the MMAs of both SMs, which halves the per-tile issue cost.
+template <int BN, int KC, bool CP, bool PAIR>
 __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __grid_constant__ TcParams P) {
-  constexpr int B_BYTES = BN * KC * 2;
+  constexpr int B_BYTES = BN * KC * 2 / (PAIR ? 2 : 1);
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int bid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int gdim = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int MAX_ST = 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -872,19 +880,27 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }   // 4 warps own a tile
+    for (int s = 0; s < NACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 8 : 4); }   // 4 warps (per CTA) own a tile
     mbar_init(bfull, 1);
     mbar_init(bempty, P.res_dual ? 2 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_phase = P.tiles_n * P.tiles_x * P.tiles_y * P.tiles_b;
@@ -895,33 +911,45 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
     if (elect_one()) {
       uint32_t stage = 0, ph = 0, beph = 0;
       int cur_phase = -1;
+      const bool lead = !PAIR || crank == 0;
+      const uint32_t mult = PAIR ? 2u : 1u;
+      const uint32_t full_leader = PAIR ? mapa_u32(smem_u32(full), 0) : 0;
+      const uint32_t bfull_leader = PAIR ? mapa_u32(smem_u32(bfull), 0) : 0;
       TileIter it;
-      it.init(P, blockIdx.x, gridDim.x);
-      for (int tile = blockIdx.x; tile < P.tiles_total; tile += gridDim.x, it.next(P)) {
+      it.init(P, bid, gdim);
+      for (int tile = bid; tile < P.tiles_total; tile += gdim, it.next(P)) {
         const int phase = it.phase, bt = it.bt;
         if (phase != cur_phase) {
           if (cur_phase >= 0) { mbar_wait(bempty, beph, P.error_flag); beph ^= 1; }   // MMAs of the old phase are done
           const int nkb = P.kblocks[phase];
-          mbar_expect_tx(bfull, (uint32_t)(nkb * B_BYTES));
-          for (int kb = 0; kb < nkb; ++kb)
-            tma_load_2d(smem_b + kb * B_BYTES, &P.tmB, bfull, 0, (P.wkb_phase0[phase] + kb) * P.cout_pad);
+          if (lead) mbar_expect_tx(bfull, mult * (uint32_t)(nkb * B_BYTES));
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int row = (P.wkb_phase0[phase] + kb) * P.cout_pad + (PAIR ? crank * (BN / 2) : 0);
+            if constexpr (PAIR) tma2_load_2d(smem_b + kb * B_BYTES, &P.tmB, bfull_leader, 0, row);
+            else tma_load_2d(smem_b + kb * B_BYTES, &P.tmB, bfull, 0, row);
+          }
           cur_phase = phase;
         }
-        const int x0 = it.xt * P.TW, y0 = it.yt * P.TH;
+        const int x0 = (PAIR ? 2 * it.xt + crank : it.xt) * P.TW, y0 = it.yt * P.TH;
         const int ns = s_nsteps[phase];
-        if (tile == (int)blockIdx.x) pdl_wait();     // the weights above are static; activations come from the previous kernel
+        if (tile == bid) pdl_wait();     // the weights above are static; activations come from the previous kernel
         for (int i = 0; i < ns; ++i) {
           const Step& sp = s_steps[phase * kMaxSteps + i];
           mbar_wait(&empty[stage], ph ^ 1, P.error_flag);
           const bool skip_a = P.dbg_mode == 3 || P.dbg_mode == 5;     // experiment: activation fill switched off
-          mbar_expect_tx(&full[stage], skip_a ? 0u : sp.bytes);
+          if (lead) mbar_expect_tx(&full[stage], skip_a ? 0u : mult * sp.bytes);
           void* da = smem_a + stage * a_stage;
           if (skip_a) {
+          } else if constexpr (PAIR) {
+            if (sp.mode == 0)
+              tma2_load_4d(da, &P.tmA[sp.src], full_leader + 8 * stage, sp.c0, x0 + sp.ox, y0 + sp.oy, bt);
+            else
+              tma2_load_5d(da, &P.tmA[sp.src], full_leader + 8 * stage, sp.c0, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
           } else if (sp.mode == 0)
             tma_load_4d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, y0 + sp.oy, bt);
           else
             tma_load_5d(da, &P.tmA[sp.src], &full[stage], sp.c0, x0 + sp.ox, sp.py, y0 + sp.oy, bt);
-          dbg_stamp(P, 0, (tile - blockIdx.x) / gridDim.x, i);
+          dbg_stamp(P, 0, (tile - bid) / gdim, i);
           if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
         }
       }
@@ -935,11 +963,11 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
     const bool dual = P.res_dual != 0;
     // Two issuers are only safe when they never share a pipeline stage (an mbarrier waiter must not run a whole
     // phase ahead of the barrier): the host enables `res_dual` iff stages % (2 * steps_per_tile) == 0.
-    if ((dual || r == 0) && elect_one()) {
-      constexpr uint32_t idesc = instr_desc<BN>();
+    if ((dual || r == 0) && (!PAIR || crank == 0) && elect_one()) {
+      constexpr uint32_t idesc = instr_desc<BN, PAIR ? 256 : 128>();
       constexpr int NK = KC / 16;
       const uint64_t desc_hi_lo = make_smem_desc<KC>(0);          // all fields except the start address
-      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+      const uint32_t a_base = smem_u32(smem_a) & 0x3FFFF, b_base = smem_u32(smem_b) & 0x3FFFF;
       const uint32_t desc_hi_fixed = (uint32_t)(desc_hi_lo >> 32) & ~0x3fffu;   // version + swizzle mode
       const uint32_t b_hi = (uint32_t)(desc_hi_lo >> 32);
       const uint32_t b_lo0 = (b_base >> 4) | 0x10000u;
@@ -948,9 +976,9 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
       const int total = P.tiles_total, tn = P.tiles_n, tX = P.tiles_x, tY = P.tiles_y, tB = P.tiles_b;
       int32_t* const perr = P.error_flag;
       TileIter it;
-      it.init(P, blockIdx.x, gridDim.x);
+      it.init(P, bid, gdim);
       int li = 0;                                                   // local tile index
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, it.next(tn, tX, tY, tB), ++li) {
+      for (int tile = bid; tile < total; tile += gdim, it.next(tn, tX, tY, tB), ++li) {
         const int phase = it.phase;
         const int ns = s_nsteps[phase];
         const bool mine = dual ? ((li & 1) == r) : true;
@@ -988,34 +1016,43 @@ __global__ void __launch_bounds__(kThreadsRes, 1) conv_tc_res_kernel(const __gri
                 const uint32_t b_lo = b_lo0 + (tw[t] >> 16) * (uint32_t)(B_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                  umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
+                  if constexpr (PAIR)
+                    umma2_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
+                  else
+                    umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc);
                   acc = 1;
                 }
               }
             }
-            umma_commit(&empty[stage]);
+            if constexpr (PAIR) umma2_commit(&empty[stage]); else umma_commit(&empty[stage]);
             if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
           }
-          umma_commit(&tfull[as]);
+          if constexpr (PAIR) umma2_commit(&tfull[as]); else umma_commit(&tfull[as]);
           dbg_stamp(P, 1, li, 6);
         } else {
           // the other issuer's tile: only track which pipeline stages it consumes
           for (int i = 0; i < ns; ++i)
             if (++stage == (uint32_t)stages) { stage = 0; ph ^= 1; }
         }
-        const int next = tile + gridDim.x;
-        if (next < total && next >= (phase + 1) * tiles_per_phase) umma_commit(bempty);   // both issuers (count 2)
+        const int next = tile + gdim;
+        if (next < total && next >= (phase + 1) * tiles_per_phase) {                      // both issuers (count 2)
+          if constexpr (PAIR) umma2_commit(bempty); else umma_commit(bempty);
+        }
       }
     }
   } else if (warp < 10) {
-    epilogue_role<BN, 1, false, NACC, CP, true>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
+    epilogue_role<BN, 1, PAIR, NACC, CP, true>(P, tmem_base, tfull, tempty, epi_params, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -1247,6 +1284,7 @@ bool g_allow_dual = true;
 bool g_allow_pair = true;
 bool g_allow_grp = true;
 int g_direct_default = 1;
+bool g_allow_res_pair = false;     // measured slower than single-CTA tiles (0.316 vs 0.278 ms at 64->64 @256x256): kept as an experiment switch
 bool g_allow_const = true;
 bool g_grp_mixed = false;             // group layers that mix shareable (mode 0) and stride-2-sampled (mode 1) taps
 int g_grp_halo = 1;                  // 1: grouped streaming kernel uses 8-pixel-wide tiles with a full (x and y) halo box
@@ -1494,7 +1532,10 @@ Plan build_plan_impl(const disco_conv_desc* d, bool allow_grp) {
   }
   const int epi_cols = p.BN;       // alternating epilogue: every warp owns all columns of its tiles
   const int epi_bytes = 8 * (3 * epi_cols + (p.gray_src >= 0 ? 9 * epi_cols : 0)) * 4 + 8 * 2048;
-  const int fixed = b_bytes + 256 + epi_bytes + 1024;
+  // CTA pairs (cta_group::2) for the 64-channel layers: each CTA keeps half of every weight block
+  p.pair = g_allow_pair && g_allow_res_pair && p.BN == 64 && ((p.Wg + TW - 1) / TW) % 2 == 0;
+  const int b_res = p.pair ? b_bytes / 2 : b_bytes;
+  const int fixed = b_res + 256 + epi_bytes + 1024;
   int stages = (225 * 1024 - fixed) / a_stage;
   if (stages > 8) stages = 8;
   if (stages < 2) return p;
@@ -1510,7 +1551,7 @@ Plan build_plan_impl(const disco_conv_desc* d, bool allow_grp) {
     }
   }
   p.resident = true;
-  p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_bytes;
+  p.res_stages = stages; p.res_a_stage_bytes = a_stage; p.res_b_bytes = b_res;
   p.res_smem_bytes = stages * a_stage + fixed;
   return p;
 }
@@ -1615,19 +1656,24 @@ int launch_pair_cfg(const TcParams& P, int grid, cudaStream_t st) {
   return launch_tc(conv_tc_kernel<BN, KC, MT, true>, P, grid, kThreads, C::SMEM_BYTES, 2, st);
 }
 
-template <int BN, int KC, bool CP>
+template <int BN, int KC, bool CP, bool PAIR>
 int launch_res_cfg2(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC, CP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_bytes = smem_bytes;
   }
-  return launch_tc(conv_tc_res_kernel<BN, KC, CP>, P, grid, kThreadsRes, (size_t)smem_bytes, 1, st);
+  return launch_tc(conv_tc_res_kernel<BN, KC, CP, PAIR>, P, grid, kThreadsRes, (size_t)smem_bytes, PAIR ? 2 : 1, st);
 }
 template <int BN, int KC>
-int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
-  return P.const_params ? launch_res_cfg2<BN, KC, true>(P, grid, smem_bytes, st)
-                        : launch_res_cfg2<BN, KC, false>(P, grid, smem_bytes, st);
+int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
+  if constexpr (BN == 64) {
+    if (pair)
+      return P.const_params ? launch_res_cfg2<BN, KC, true, true>(P, grid, smem_bytes, st)
+                            : launch_res_cfg2<BN, KC, false, true>(P, grid, smem_bytes, st);
+  }
+  return P.const_params ? launch_res_cfg2<BN, KC, true, false>(P, grid, smem_bytes, st)
+                        : launch_res_cfg2<BN, KC, false, false>(P, grid, smem_bytes, st);
 }
 
 template <int BN, int KC, int MT, bool PAIR>
@@ -1652,11 +1698,11 @@ int launch_grp(const Plan& pl, const TcParams& P, int grid, cudaStream_t st) {
 }
 
 template <int KC>
-int launch_res_bn(int BN, const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+int launch_res_bn(int BN, const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
   switch (BN) {
-    case 16: return launch_res_cfg<16, KC>(P, grid, smem_bytes, st);
-    case 32: return launch_res_cfg<32, KC>(P, grid, smem_bytes, st);
-    case 64: return launch_res_cfg<64, KC>(P, grid, smem_bytes, st);
+    case 16: return launch_res_cfg<16, KC>(P, grid, smem_bytes, pair, st);
+    case 32: return launch_res_cfg<32, KC>(P, grid, smem_bytes, pair, st);
+    case 64: return launch_res_cfg<64, KC>(P, grid, smem_bytes, pair, st);
   }
   disco_set_error("conv_tc: unsupported resident BN %d", BN);
   return DISCO_ERR_INVALID;
@@ -1749,6 +1795,8 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
     const char* pr = getenv("DISCO_TC_PAIR");
     if (pr && pr[0] == '0') g_allow_pair = false;
     if (getenv("DISCO_TC_PAIR_MIN_KB")) g_pair_min_kb = atoi(getenv("DISCO_TC_PAIR_MIN_KB"));
+    const char* rp = getenv("DISCO_TC_RES_PAIR");
+    if (rp) g_allow_res_pair = rp[0] != '0';
     const char* pd = getenv("DISCO_TC_PDL");
     if (pd && pd[0] == '0') g_allow_pdl = false;
     const char* cp = getenv("DISCO_TC_CONST");
@@ -1889,9 +1937,9 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   int rc;
   if (c.plan.resident) {
     switch (c.plan.KC) {
-      case 64: rc = launch_res_bn<64>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
-      case 32: rc = launch_res_bn<32>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
-      case 16: rc = launch_res_bn<16>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, st); break;
+      case 64: rc = launch_res_bn<64>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
+      case 32: rc = launch_res_bn<32>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
+      case 16: rc = launch_res_bn<16>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
       default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
     }
   } else if (c.plan.grouped) {
