@@ -3,6 +3,7 @@
 // decisions -- k-means assignments, argmax labels -- so it is kept in full precision).
 #include "common.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace {
 
@@ -247,8 +248,7 @@ __global__ void __launch_bounds__(256) encoder_tail_kernel(const EncTailArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
-// attention core: grid (B*8, ceil(S/128)), 128 threads, thread = query; K/V of the head in smem.
-// One pass over the keys with a running maximum (online softmax, fp32), four keys per iteration for ILP.
+// attention helpers (fp32)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float dot8(const float (&q)[8], const float* k) {
   const float4 a = *reinterpret_cast<const float4*>(k);
@@ -265,36 +265,34 @@ __device__ __forceinline__ void axpy8(float (&o)[8], float p, const float* v) {
   o[4] = fmaf(p, b.x, o[4]); o[5] = fmaf(p, b.y, o[5]); o[6] = fmaf(p, b.z, o[6]); o[7] = fmaf(p, b.w, o[7]);
 }
 
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ out) {
-  extern __shared__ float kv[];   // K [S4][8] then V [S4][8], S4 = S rounded up to 4 (padding rows are zero)
-  const int S4 = (S + 3) & ~3;
-  float* Ks = kv;
-  float* Vs = kv + (size_t)S4 * 8;
-  const int n = blockIdx.x >> 3, hd = blockIdx.x & 7;
-  const float* base = qkv + (size_t)n * S * 192;
-  for (int e = threadIdx.x; e < S4 * 2; e += 128) {
-    const int t = e >> 1, half = e & 1;
-    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
-    if (t < S) {
-      k4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 64 + hd * 8 + half * 4);
-      v4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 128 + hd * 8 + half * 4);
-    }
-    *reinterpret_cast<float4*>(Ks + t * 8 + half * 4) = k4;
-    *reinterpret_cast<float4*>(Vs + t * 8 + half * 4) = v4;
-  }
-  __syncthreads();
-  const int qi = blockIdx.y * 128 + threadIdx.x;
-  if (qi >= S) return;
-  float q[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8);
-    const float4 b = *reinterpret_cast<const float4*>(base + (size_t)qi * 192 + hd * 8 + 4);
-    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
-    // scores are kept in log2 units so that the softmax exponentials are single ex2 instructions
+// Packed fp32 pairs (Blackwell FFMA2): one instruction = two fp32 FMAs, full fp32 precision.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void lds2x2(const float* p, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One query against all keys with a running maximum (online softmax): the exact fall-back of attention_kernel.
+__device__ __noinline__ void attend_online(const float (&q)[8], const float* Ks, const float* Vs, int S, int S4, float (&o)[8],
+                                           float& sum_out) {
+  float mx = -FLT_MAX, sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) q[c] *= 1.4426950408889634f;
-  }
-  float mx = -FLT_MAX, sum = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < 8; ++c) o[c] = 0.f;
   for (int j = 0; j < S4; j += 4) {
     float s0 = dot8(q, Ks + j * 8), s1 = dot8(q, Ks + j * 8 + 8), s2 = dot8(q, Ks + j * 8 + 16), s3 = dot8(q, Ks + j * 8 + 24);
     if (j + 3 >= S) {                      // tail: padded keys must not contribute
@@ -311,10 +309,120 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     axpy8(o, p0, Vs + j * 8); axpy8(o, p1, Vs + j * 8 + 8); axpy8(o, p2, Vs + j * 8 + 16); axpy8(o, p3, Vs + j * 8 + 24);
     mx = mnew;
   }
-  const float inv = 1.0f / sum;
-  float* dst = out + ((size_t)n * S + qi) * 64 + hd * 8;
-  *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+  sum_out = sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention core: grid (B*8, ceil(S / (2*blockDim))), thread = TWO queries; K/V of the (image, head) in smem.
+// softmax(s) = exp(s - m) / sum exp(s - m) for ANY reference m.  The running maximum of online softmax is a serial
+// max -> rescale chain per key group; here the reference is simply m = 0: scores are kept in log2 units, fp32 exp2 covers
+// [-126, 128), and attention logits of LayerNorm'd tokens sit far inside that range.  The rare query whose sum leaves
+// [2^-60, 2^100] (or is not finite) is recomputed with the online-softmax routine above, so the result is exact in
+// every case; the argument of every exponential is the score itself, i.e. as accurate as subtracting the true maximum.
+// The inner loop is straight-line packed-fp32 work, four keys per iteration: per (query, key) 4 FFMA2 (q.k) + add +
+// ex2 + add + pack + 4 FFMA2 (p.v), K/V rows shared by the thread's two queries.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ out) {
+  extern __shared__ float kv[];   // K [S4][8] then V [S4][8], S4 = S rounded up to 4 (padding rows are zero)
+  const int S4 = (S + 3) & ~3;
+  float* Ks = kv;
+  float* Vs = kv + (size_t)S4 * 8;
+  const int n = blockIdx.x >> 3, hd = blockIdx.x & 7;
+  const float* base = qkv + (size_t)n * S * 192;
+  for (int e = threadIdx.x; e < S4 * 2; e += blockDim.x) {
+    const int t = e >> 1, half = e & 1;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+    if (t < S) {
+      k4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 64 + hd * 8 + half * 4);
+      v4 = *reinterpret_cast<const float4*>(base + (size_t)t * 192 + 128 + hd * 8 + half * 4);
+    }
+    *reinterpret_cast<float4*>(Ks + t * 8 + half * 4) = k4;
+    *reinterpret_cast<float4*>(Vs + t * 8 + half * 4) = v4;
+  }
+  __syncthreads();
+
+  const int q0i = blockIdx.y * (2 * blockDim.x) + threadIdx.x, q1i = q0i + blockDim.x;
+  if (q0i >= S) return;
+  const bool has1 = q1i < S;
+  float qa[8], qb[8];
+  {
+    const float* p0 = base + (size_t)q0i * 192 + hd * 8;
+    const float* p1 = base + (size_t)(has1 ? q1i : q0i) * 192 + hd * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(p0), a1 = *reinterpret_cast<const float4*>(p0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p1), b1 = *reinterpret_cast<const float4*>(p1 + 4);
+    qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
+    qb[0] = b0.x; qb[1] = b0.y; qb[2] = b0.z; qb[3] = b0.w; qb[4] = b1.x; qb[5] = b1.y; qb[6] = b1.z; qb[7] = b1.w;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { qa[c] *= 1.4426950408889634f; qb[c] *= 1.4426950408889634f; }
+  }
+  f32x2 QA[4], QB[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { QA[c] = pack2(qa[2 * c], qa[2 * c + 1]); QB[c] = pack2(qb[2 * c], qb[2 * c + 1]); }
+  const f32x2 zero2 = pack2(0.f, 0.f);
+  f32x2 OA[4], OB[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { OA[c] = zero2; OB[c] = zero2; }
+  float suma = 0.f, sumb = 0.f;
+  for (int j = 0; j < S4; j += 4) {
+    f32x2 K[4][4], V[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lds2x2(Ks + (j + u) * 8, K[u][0], K[u][1]);
+      lds2x2(Ks + (j + u) * 8 + 4, K[u][2], K[u][3]);
+      lds2x2(Vs + (j + u) * 8, V[u][0], V[u][1]);
+      lds2x2(Vs + (j + u) * 8 + 4, V[u][2], V[u][3]);
+    }
+    f32x2 sa[4], sb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { sa[u] = ffma2(QA[0], K[u][0], zero2); sb[u] = ffma2(QB[0], K[u][0], zero2); }
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sa[u] = ffma2(QA[c], K[u][c], sa[u]); sb[u] = ffma2(QB[c], K[u][c], sb[u]); }
+    float pa[4], pb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float al, ah, bl, bh;
+      unpack2(sa[u], al, ah);
+      unpack2(sb[u], bl, bh);
+      pa[u] = ex2f(al + ah);
+      pb[u] = ex2f(bl + bh);
+    }
+    if (j + 4 > S) {                       // tail: padded (all-zero) keys must not contribute
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (j + u >= S) { pa[u] = 0.f; pb[u] = 0.f; }
+    }
+    suma += (pa[0] + pa[1]) + (pa[2] + pa[3]);
+    sumb += (pb[0] + pb[1]) + (pb[2] + pb[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const f32x2 PA = pack2(pa[u], pa[u]), PB = pack2(pb[u], pb[u]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { OA[c] = ffma2(PA, V[u][c], OA[c]); OB[c] = ffma2(PB, V[u][c], OB[c]); }
+    }
+  }
+  float oa[8], ob[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { unpack2(OA[c], oa[2 * c], oa[2 * c + 1]); unpack2(OB[c], ob[2 * c], ob[2 * c + 1]); }
+  // validity of the m = 0 evaluation: the sum stayed inside [2^-60, 2^100] and the outputs are finite; otherwise exact path
+  float ca = 0.f, cb = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { ca += fabsf(oa[c]); cb += fabsf(ob[c]); }
+  if (!(suma >= 8.67e-19f && suma <= 1.2e30f && ca <= 3.0e38f)) attend_online(qa, Ks, Vs, S, S4, oa, suma);
+  if (has1 && !(sumb >= 8.67e-19f && sumb <= 1.2e30f && cb <= 3.0e38f)) attend_online(qb, Ks, Vs, S, S4, ob, sumb);
+  {
+    const float inv = 1.0f / suma;
+    float* dst = out + ((size_t)n * S + q0i) * 64 + hd * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(oa[0] * inv, oa[1] * inv, oa[2] * inv, oa[3] * inv);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(oa[4] * inv, oa[5] * inv, oa[6] * inv, oa[7] * inv);
+  }
+  if (has1) {
+    const float inv = 1.0f / sumb;
+    float* dst = out + ((size_t)n * S + q1i) * 64 + hd * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(ob[0] * inv, ob[1] * inv, ob[2] * inv, ob[3] * inv);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(ob[4] * inv, ob[5] * inv, ob[6] * inv, ob[7] * inv);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -604,8 +712,12 @@ extern "C" int disco_attention(disco_handle* h, const float* qkv, int batch, int
   DISCO_CHECK_ARG(smem <= 200 * 1024, "attention: S=%d too large for the shared-memory K/V stage", S);
   if (smem > 48 * 1024)
     DISCO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(batch * 8, (S + 127) / 128);
-  attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, S, out);
+  // two queries per thread, 128-thread CTAs (measured best of 32/64/128/256 at both S = 256 and S = 1024: enough CTAs
+  // for an even spread over the SMs, K/V stage shared by 256 queries)
+  int threads = 128;
+  if (const char* e = getenv("DISCO_ATT_THREADS")) threads = atoi(e);
+  dim3 grid(batch * 8, (S + 2 * threads - 1) / (2 * threads));
+  attention_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(qkv, S, out);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }

@@ -1,4 +1,7 @@
-mkdir -p gpurun_out
-P="python -m disentangledcolorization_b200.tools.conv_probe"
-DISCO_TC_DEBUG=1 timeout 60 $P --cin 64 --cout 64 --hw 256 --batch 64 --iters 3 > gpurun_out/tl_64e.log 2>&1
-tail -1 gpurun_out/tl_64e.log
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 280 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_att.json 2> gpurun_out/bench_att.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_att.json').read())
+print(d['ms_per_step'], d['value'], d['e2e']['value'])
+PY

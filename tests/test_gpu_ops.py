@@ -257,3 +257,51 @@ def test_token_labels():
     ab = (torch.rand(B, 2, h, w, generator=g) - 0.5) * 0.8
     hard = basic.ColorLabel().encode_ab2ind_hard(ab.cuda())
     assert torch.equal(hard.cpu(), O.encode_ab2ind(ab).max(dim=1, keepdim=True)[1])
+
+
+def _attention_ref(qkv, B, S):
+    """softmax(q k^T) v per (image, head) in float64; q is already scaled (the QKV projection folds 1/sqrt(d_head))."""
+    x = qkv.double().view(B, S, 3, 8, 8)
+    q, k, v = x[:, :, 0].permute(0, 2, 1, 3), x[:, :, 1].permute(0, 2, 1, 3), x[:, :, 2].permute(0, 2, 1, 3)   # B,8,S,8
+    att = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v
+    return att.permute(0, 2, 1, 3).reshape(B * S, 64)
+
+
+@pytest.mark.parametrize("B,S", [(2, 24), (1, 100), (3, 256), (1, 1024), (1, 1030)], ids=str)
+def test_attention_matches_float64_softmax(B, S):
+    """disco_attention (two queries per thread, packed fp32 FMAs, fixed softmax reference m = 0 with exact fall-back)
+    against float64 softmax attention: ragged token counts, both CTA shapes (S <= 256 and S > 256)."""
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(1000 + S)
+    qkv = torch.randn(B * S, 192, generator=g)
+    qkv[:, :64] *= 1.5
+    hd = _handle()
+    out = torch.empty(B * S, 64, device="cuda")
+    d = qkv.cuda()
+    _lib.check(hd.lib.disco_attention(hd.h, C.c_void_p(d.data_ptr()), B, S, C.c_void_p(out.data_ptr()), _stream()), "attention")
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv, B, S)
+    assert (out.cpu().double() - ref).abs().max() < 5e-6
+
+
+def test_attention_falls_back_outside_the_exp2_range():
+    """Scores beyond fp32 exp2's range (one head overflows: |s| ~ 500 log2 units; another underflows: all scores ~ -500)
+    invalidate the m = 0 evaluation: the online-softmax routine must take over for exactly those queries."""
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(77)
+    B, S = 1, 64
+    qkv = torch.randn(B * S, 192, generator=g)
+    x = qkv.view(S, 3, 8, 8)
+    x[:, 0, 1] *= 60.0             # head 1: scores of magnitude ~ +-500 (overflow AND underflow of exp2 without a reference)
+    x[:, 1, 2] = -torch.abs(x[:, 1, 2])
+    x[:, 0, 2] = 40.0 * torch.abs(x[:, 0, 2])   # head 2: every score strongly negative (sum underflows to 0)
+    x[9, 1, 3, :] = 40.0 * x[2, 0, 3, :] / x[2, 0, 3, :].norm()   # head 3: one genuinely large score (sharp softmax)
+    hd = _handle()
+    out = torch.empty(B * S, 64, device="cuda")
+    d = qkv.cuda()
+    _lib.check(hd.lib.disco_attention(hd.h, C.c_void_p(d.data_ptr()), B, S, C.c_void_p(out.data_ptr()), _stream()), "attention")
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv, B, S)
+    assert torch.isfinite(out).all()
+    # scores of magnitude ~500 carry ~3e-5 of fp32 rounding themselves: this test is about the fall-back logic
+    assert (out.cpu().double() - ref).abs().max() < 1e-4
