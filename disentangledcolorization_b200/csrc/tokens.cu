@@ -169,71 +169,75 @@ __global__ void __launch_bounds__(256) encoder_tail_kernel(const EncTailArgs a) 
   const int lr = tid >> 2, lc = (tid & 3) * 4;   // load role: row lr, k offset lc..lc+3
   float acc[4][4];
 
-  // ---- phase 1: x1 = LN1(x + att Wo^T + bo)
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < 64; k0 += 16) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m0 + lr < a.M) v = *reinterpret_cast<const float4*>(a.att + (size_t)(m0 + lr) * 64 + k0 + lc);
-    As[lc + 0][lr] = v.x; As[lc + 1][lr] = v.y; As[lc + 2][lr] = v.z; As[lc + 3][lr] = v.w;
-    const float4 wv = *reinterpret_cast<const float4*>(a.wo + (size_t)lr * 64 + k0 + lc);
-    Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
-    __syncthreads();
-    mm_chunk(As, 0, Bs, tx, ty, acc);
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = ty * 4 + i;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = tx * 4 + j;
-      float v = acc[i][j] + a.bo[c];
-      if (m0 + r < a.M) v += a.x[(size_t)(m0 + r) * 64 + c];
-      Cs[r][c] = v;
+  // The three GEMMs consume 36 weight tiles of 64 rows x 16 k (4 of Wo, 16 of W1, 16 of W2).  The tile of step s+1
+  // (and, in phase 1, the matching slice of the attention output) is fetched into registers BEFORE the FMAs of step s,
+  // so the L2 latency of the weight stream is off the critical path.  Measured neutral (52 us per launch at M = 16384
+  // either way): ncu shows the kernel bound by the shared-memory pipe -- a 4x4 register tile costs two LDS.128 = 8
+  // wavefronts per 16 FFMA (62 k LSU wavefronts per SM in 103 k cycles, FMA pipe 39 %); the next step for the token
+  // GEMMs is a tensor-core formulation with split-bf16 operands, not more SIMT tuning.
+  constexpr int kSteps = 36;
+  auto load_w = [&](int step) -> float4 {
+    if (step < 4) return *reinterpret_cast<const float4*>(a.wo + (size_t)lr * 64 + step * 16 + lc);
+    if (step < 20) {
+      const int nb = (step - 4) >> 2, k0 = ((step - 4) & 3) * 16;
+      return *reinterpret_cast<const float4*>(a.w1 + (size_t)(nb * 64 + lr) * 64 + k0 + lc);
     }
-  }
-  __syncthreads();
-  ln_rows(Cs, a.g1, a.be1, X1T, nullptr, m0, a.M, tid);
-
-  // ---- phase 2: hidden = relu(x1 W1^T + b1), four 64-column blocks
-  for (int nb = 0; nb < 4; ++nb) {
+    return *reinterpret_cast<const float4*>(a.w2 + (size_t)lr * 256 + (step - 20) * 16 + lc);
+  };
+  auto load_att = [&](int step) -> float4 {
+    if (m0 + lr < a.M) return *reinterpret_cast<const float4*>(a.att + (size_t)(m0 + lr) * 64 + step * 16 + lc);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto zero_acc = [&]() {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < 64; k0 += 16) {
-      const float4 wv = *reinterpret_cast<const float4*>(a.w1 + (size_t)(nb * 64 + lr) * 64 + k0 + lc);
-      Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
-      __syncthreads();
-      mm_chunk(X1T, k0, Bs, tx, ty, acc);
-      __syncthreads();
-    }
+  };
+  float4 wnext = load_w(0), anext = load_att(0);
+  zero_acc();
+  for (int step = 0; step < kSteps; ++step) {
+    Bs[lc + 0][lr] = wnext.x; Bs[lc + 1][lr] = wnext.y; Bs[lc + 2][lr] = wnext.z; Bs[lc + 3][lr] = wnext.w;
+    if (step < 4) { As[lc + 0][lr] = anext.x; As[lc + 1][lr] = anext.y; As[lc + 2][lr] = anext.z; As[lc + 3][lr] = anext.w; }
+    __syncthreads();
+    if (step + 1 < kSteps) wnext = load_w(step + 1);
+    if (step + 1 < 4) anext = load_att(step + 1);
+    if (step < 4) mm_chunk(As, 0, Bs, tx, ty, acc);                          // x + att Wo^T
+    else if (step < 20) mm_chunk(X1T, ((step - 4) & 3) * 16, Bs, tx, ty, acc);   // x1 W1^T, block nb
+    else mm_chunk(HdT, (step - 20) * 16, Bs, tx, ty, acc);                   // hidden W2^T
+    __syncthreads();
+    if (step == 3) {
+      // ---- end of phase 1: x1 = LN1(x + att Wo^T + bo)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = nb * 64 + tx * 4 + j;
-        const float v = acc[i][j] + a.b1[c];
-        HdT[c][ty * 4 + i] = v > 0.f ? v : 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const int c = tx * 4 + j;
+          float v = acc[i][j] + a.bo[c];
+          if (m0 + r < a.M) v += a.x[(size_t)(m0 + r) * 64 + c];
+          Cs[r][c] = v;
+        }
       }
-  }
-  __syncthreads();
-
-  // ---- phase 3: y = LN2(x1 + hidden W2^T + b2)
+      __syncthreads();
+      ln_rows(Cs, a.g1, a.be1, X1T, nullptr, m0, a.M, tid);
+      zero_acc();
+    } else if (step >= 4 && step < 20 && ((step - 4) & 3) == 3) {
+      // ---- end of one 64-column block of phase 2: hidden = relu(x1 W1^T + b1)
+      const int nb = (step - 4) >> 2;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < 256; k0 += 16) {
-    const float4 wv = *reinterpret_cast<const float4*>(a.w2 + (size_t)lr * 256 + k0 + lc);
-    Bs[lc + 0][lr] = wv.x; Bs[lc + 1][lr] = wv.y; Bs[lc + 2][lr] = wv.z; Bs[lc + 3][lr] = wv.w;
-    __syncthreads();
-    mm_chunk(HdT, k0, Bs, tx, ty, acc);
-    __syncthreads();
+        for (int j = 0; j < 4; ++j) {
+          const int c = nb * 64 + tx * 4 + j;
+          const float v = acc[i][j] + a.b1[c];
+          HdT[c][ty * 4 + i] = v > 0.f ? v : 0.f;
+        }
+      zero_acc();
+      if (step == 19) __syncthreads();
+    }
   }
+  // ---- end of phase 3: y = LN2(x1 + hidden W2^T + b2)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = ty * 4 + i;
@@ -265,19 +269,6 @@ __device__ __forceinline__ void axpy8(float (&o)[8], float p, const float* v) {
   o[4] = fmaf(p, b.x, o[4]); o[5] = fmaf(p, b.y, o[5]); o[6] = fmaf(p, b.z, o[6]); o[7] = fmaf(p, b.w, o[7]);
 }
 
-// Packed fp32 pairs (Blackwell FFMA2): one instruction = two fp32 FMAs, full fp32 precision.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ void lds2x2(const float* p, f32x2& a, f32x2& b) {
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
