@@ -430,8 +430,32 @@ struct KmArgs {
 
 // Runs one image.  XT: optional shared-memory copy of the image's tokens, transposed and padded:
 // XT[c * (S + 1) + t] (conflict-free for both "thread = token" and "thread = (cluster, channel)" access).
+// Assignment step for K <= KT clusters: squared distances accumulated channel by channel (same order for every KT, so the
+// specialisations are bit-identical), first minimum wins like torch.argmin.
+template <int KT>
+__device__ __forceinline__ void kmeans_assign(const float* __restrict__ X, const float* XT, const float* C, int S, int K, int SP1,
+                                              int* s_assign, int32_t* __restrict__ assign, int tid, int nt) {
+  for (int t = tid; t < S; t += nt) {
+    float dk[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) dk[k] = 0.f;
+    for (int c = 0; c < KD; ++c) {
+      const float xv = XT ? XT[c * SP1 + t] : X[(size_t)t * KD + c];
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) { const float df = xv - C[k * KD + c]; dk[k] = fmaf(df, df, dk[k]); }
+    }
+    float best = FLT_MAX; int bi = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K && dk[k] < best) { best = dk[k]; bi = k; }
+    if (s_assign) s_assign[t] = bi;
+    assign[t] = bi;
+  }
+}
+
 __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float* C, float* Cprev, int* cnt,
-                                 int* ridx, float* shiftk, int* s_flag, float* XT, int* s_assign) {
+                                 int* ridx, float* shiftk, int* s_flag, float* XT, int* s_assign, int* members, int* moff) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int S = a.S, K = a.K, SP1 = S + 1;
   const float* X = a.X + (size_t)n * S * KD;
@@ -443,24 +467,10 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
   if (tid == 0) { s_flag[0] = 0; /* events */ s_flag[1] = 0; /* stop */ s_flag[2] = 0; /* iterations */ }
   __syncthreads();
   while (true) {
-    // 1. assignment (first minimum wins, like torch.argmin)
-    for (int t = tid; t < S; t += nt) {
-      float dk[KMAX];
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) dk[k] = 0.f;
-      for (int c = 0; c < KD; ++c) {
-        const float xv = XT ? XT[c * SP1 + t] : X[(size_t)t * KD + c];
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) { const float df = xv - C[k * KD + c]; dk[k] = fmaf(df, df, dk[k]); }
-      }
-      float best = FLT_MAX; int bi = 0;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K && dk[k] < best) { best = dk[k]; bi = k; }
-      if (s_assign) s_assign[t] = bi;
-      assign[t] = bi;
-    }
+    // 1. assignment (first minimum wins, like torch.argmin); the unrolled cluster loop is sized to K
+    if (K <= 8) kmeans_assign<8>(X, XT, C, S, K, SP1, s_assign, assign, tid, nt);
+    else if (K <= 16) kmeans_assign<16>(X, XT, C, S, K, SP1, s_assign, assign, tid, nt);
+    else kmeans_assign<KMAX>(X, XT, C, S, K, SP1, s_assign, assign, tid, nt);
     for (int e = tid; e < K * KD; e += nt) Cprev[e] = C[e];
     __syncthreads();
     // 2. member counts (one warp per cluster), then draws for empty clusters in cluster order
@@ -478,6 +488,8 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
     }
     __syncthreads();
     if (tid == 0) {
+      int off = 0;
+      for (int k = 0; k < K; ++k) { moff[k] = off; off += cnt[k]; }
       for (int k = 0; k < K; ++k) {
         ridx[k] = -1;
         if (cnt[k] == 0) {
@@ -488,6 +500,23 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
       }
     }
     __syncthreads();
+    // 2b. member lists in token order (one warp per cluster, ballot scan): the centre update then walks cnt[k] members
+    //     instead of testing all S tokens for every (cluster, channel) -- same additions in the same order
+    if (members) {
+      const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+      const int* asg = s_assign ? s_assign : assign;
+      for (int k = warp; k < K; k += nw) {
+        int base = moff[k];
+        for (int t0 = 0; t0 < S; t0 += 32) {
+          const int t = t0 + lane;
+          const bool hit = t < S && asg[t] == k;
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (hit) members[base + __popc(m & ((1u << lane) - 1u))] = t;
+          base += __popc(m);
+        }
+      }
+      __syncthreads();
+    }
     // 3. centre update: mean of members in token order
     {
       const int* asg = s_assign ? s_assign : assign;
@@ -498,7 +527,16 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
           v = X[(size_t)ridx[k] * KD + c];
         } else {
           float s = 0.f;
-          if (XT) {
+          if (members) {
+            const int* ml = members + moff[k];
+            const int m = cnt[k];
+            if (XT) {
+              const float* col = XT + c * SP1;
+              for (int i = 0; i < m; ++i) s += col[ml[i]];
+            } else {
+              for (int i = 0; i < m; ++i) s += X[(size_t)ml[i] * KD + c];
+            }
+          } else if (XT) {
             const float* col = XT + c * SP1;
             for (int t = 0; t < S; ++t) if (asg[t] == k) s += col[t];
           } else {
@@ -558,7 +596,7 @@ __device__ void kmeans_one_image(const KmArgs& a, int n, int draw_offset, float*
 }
 
 // mode 0: grid B, speculative (draw offset 0).  mode 1: grid 1, sequential fix-up in image order.
-// Dynamic shared memory (when it fits): transposed tokens XT[64][S+1] followed by int assign[S].
+// Dynamic shared memory: [transposed tokens XT[64][S+1] when they fit] int assign[S], int members[S].
 __global__ void __launch_bounds__(512) kmeans_anchor_kernel(const KmArgs a, int mode, int use_smem) {
   __shared__ float C[KMAX * KD];
   __shared__ float Cprev[KMAX * KD];
@@ -566,16 +604,18 @@ __global__ void __launch_bounds__(512) kmeans_anchor_kernel(const KmArgs a, int 
   __shared__ int ridx[KMAX];
   __shared__ float shiftk[KMAX];
   __shared__ int s_flag[4];
+  __shared__ int moff[KMAX];
   extern __shared__ float km_dyn[];
   float* XT = use_smem ? km_dyn : nullptr;
-  int* s_assign = use_smem ? reinterpret_cast<int*>(km_dyn + KD * (a.S + 1)) : nullptr;
+  int* s_assign = reinterpret_cast<int*>(km_dyn + (use_smem ? KD * (a.S + 1) : 0));
+  int* members = s_assign + a.S;
   if (mode == 0) {
-    kmeans_one_image(a, blockIdx.x, 0, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign);
+    kmeans_one_image(a, blockIdx.x, 0, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign, members, moff);
   } else {
     int running = 0;
     for (int n = 0; n < a.B; ++n) {
       const int ev = a.events[n];
-      if (ev > 0 && running > 0) kmeans_one_image(a, n, running, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign);
+      if (ev > 0 && running > 0) kmeans_one_image(a, n, running, C, Cprev, cnt, ridx, shiftk, s_flag, XT, s_assign, members, moff);
       __syncthreads();
       running += a.events[n];
       __syncthreads();
@@ -722,13 +762,16 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   KmArgs a{X, init_idx, draws, n_draws, sizes, batch, S, K, iter_limit, tol, assign, hint_mask, events, iters};
   cudaStream_t st = (cudaStream_t)stream;
   DISCO_CUDA(cudaMemsetAsync(events, 0, sizeof(int32_t) * (batch + 2), st));
-  const size_t dyn = ((size_t)KD * (S + 1) + S) * sizeof(float);
-  const int use_smem = dyn <= 160 * 1024;
-  if (use_smem && dyn > 32 * 1024)
+  // dynamic smem: [XT (64 x (S+1) floats) when it fits] + assign[S] + members[S]
+  const size_t dyn_full = ((size_t)KD * (S + 1) + 2 * (size_t)S) * sizeof(float);
+  const int use_smem = dyn_full <= 160 * 1024;
+  const size_t dyn = use_smem ? dyn_full : 2 * (size_t)S * sizeof(int);
+  DISCO_CHECK_ARG(dyn <= 160 * 1024, "kmeans: S=%d too large", S);
+  if (dyn > 32 * 1024)
     DISCO_CUDA(cudaFuncSetAttribute(kmeans_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  kmeans_anchor_kernel<<<batch, 512, use_smem ? dyn : 0, st>>>(a, 0, use_smem);
+  kmeans_anchor_kernel<<<batch, 512, dyn, st>>>(a, 0, use_smem);
   DISCO_LAUNCH_CHECK(h);
-  kmeans_anchor_kernel<<<1, 512, use_smem ? dyn : 0, st>>>(a, 1, use_smem);
+  kmeans_anchor_kernel<<<1, 512, dyn, st>>>(a, 1, use_smem);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }
