@@ -104,6 +104,8 @@ PLAIN = [
     # CTA-pair (cta_group::2) variant: wide N, even number of tile columns; ragged rows; stride 2; 256-pixel sub-tiles
     (256, 256, 2, 16, 64, 1), (128, 256, 1, 32, 64, 2), (128, 128, 2, 64, 64, 1), (64, 128, 1, 64, 64, 2),
     (256, 256, 1, 20, 32, 1), (512, 512, 1, 8, 96, 1), (128, 128, 3, 40, 32, 1),
+    # stride-2 layers through the grouped kernel (parity-plane halo boxes): ragged rows, two n-tiles, odd/even tile columns
+    (64, 128, 2, 48, 32, 2), (256, 512, 1, 32, 32, 2), (128, 128, 1, 32, 96, 2), (64, 256, 1, 64, 48, 2),
 ]
 
 
