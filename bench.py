@@ -319,7 +319,9 @@ def run_ours(args):
         if args.dump_profile:
             with open(args.dump_profile, "w") as f:
                 json.dump({"ms_per_step": ms / args.steps, "conv_ms": conv_ms, "per_op": prof["per_op"]}, f, indent=1)
-        cpu_v, cores, cpu_s = (0.0, os.cpu_count(), 0.0) if args.no_cpu_baseline else cpu_oracle_throughput(CPU_SAMPLE_IMAGES)
+        # the CPU leg runs at N = 1 only (at N > 1 the other ranks would sit in the final barrier while rank 0 computes)
+        skip_cpu = args.no_cpu_baseline or world > 1
+        cpu_v, cores, cpu_s = (None, os.cpu_count(), 0.0) if skip_cpu else cpu_oracle_throughput(CPU_SAMPLE_IMAGES)
         log("cpu baseline done")
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -360,8 +362,9 @@ def run_ours(args):
                          "whole_step_frac_vs_sustained_peak": (B * FLOP_PER_IMAGE / (ms / args.steps / 1e3) / 1e12) / peak_sust,
                          "top": prof["top"]},
             "cpu_baseline": {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{CPU_SAMPLE_IMAGES} of the {B} images of a step ({H}x{W}, fed 8 at a time), oracle port of the "
-                                       f"reference forward, fp32 torch CPU, {cpu_s:.1f} s"},
+                             "sample": (f"{CPU_SAMPLE_IMAGES} of the {B} images of a step ({H}x{W}, fed 8 at a time), oracle port of the "
+                                        f"reference forward, fp32 torch CPU, {cpu_s:.1f} s") if not skip_cpu
+                             else "not run (measured at N=1 only; see the N=1 line)"},
         }
     if world > 1:
         dist.barrier()
