@@ -11,14 +11,14 @@ LIB_PATH = os.path.join(_HERE, "libdisco_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-HEAD_NONE, HEAD_SOFTMAX9, HEAD_TANH2 = 0, 1, 2
+HEAD_NONE, HEAD_SOFTMAX9, HEAD_TANH2, HEAD_RAW2 = 0, 1, 2, 3
 CONV3, DECONV4 = 0, 1
 
 EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create", "disco_destroy", "disco_launch_count",
            "disco_reset_launch_count", "disco_add_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
-           "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail"]
+           "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows"]
 
 
 class ConvSrc(C.Structure):
@@ -76,6 +76,8 @@ def load():
     lib.disco_conv_tc_weight_elems.argtypes = [C.POINTER(ConvDesc)]
     lib.disco_conv_tc_weight_elems.restype = C.c_int64
     lib.disco_conv_tc_pack_weights.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]
+    lib.disco_conv_tc_cache_clear.argtypes = [C.c_void_p]
+    lib.disco_host_choice_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)] + [C.c_int] * 5 + [C.c_void_p]
     lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
     lib.disco_linear.argtypes = [C.c_void_p, C.POINTER(LinearDesc), C.c_void_p]
@@ -117,3 +119,22 @@ class Handle:
 
     def reset_launches(self):
         self.lib.disco_reset_launch_count(self.h)
+
+
+def choice_rows(n_tokens, n_clusters, rows, keep=None):
+    """`rows` x np.random.choice(n_tokens, n_clusters, replace=False) on numpy's global generator, in one native call
+    (disco_host_choice_rows): same numbers, same final generator state, ~15x less host time.  Returns int32 (n_keep, K)
+    for rows keep=(lo, hi) (default: all).  Falls back to the python loop for a non-MT19937 global generator."""
+    import numpy as np
+    lo, hi = (0, rows) if keep is None else keep
+    st = np.random.get_state()
+    if st[0] != "MT19937":
+        allidx = [np.random.choice(n_tokens, n_clusters, replace=False) for _ in range(rows)]
+        return np.stack(allidx[lo:hi]).astype(np.int32) if hi > lo else np.zeros((0, n_clusters), np.int32)
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(st[2]))
+    out = np.empty((hi - lo, n_clusters), np.int32)
+    check(load().disco_host_choice_rows(C.c_void_p(key.ctypes.data), C.byref(pos), int(n_tokens), int(n_clusters), int(rows),
+                                        int(lo), int(hi), C.c_void_p(out.ctypes.data)), "disco_host_choice_rows")
+    np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+    return out

@@ -13,9 +13,26 @@ struct disco_handle {
   int64_t launches;
   void* tmap_encode;   // cuTensorMapEncodeTiled entry point (resolved lazily)
   bool use_tc;         // route supported bf16 descriptors to the tcgen05 kernel
+  // Per-device state (one handle per (process, device)): the opt-in dynamic shared-memory size of a kernel is a
+  // per-device attribute, and the watchdog flag the tensor-core kernels raise lives in this device's memory.
+  void* smem_attr;     // std::map<const void*, int>*: largest MaxDynamicSharedMemorySize set per kernel on this device
+  int32_t* error_flag; // device int32, 0 = ok (set by the mbarrier watchdog before it traps)
 };
 
 void disco_set_error(const char* fmt, ...);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size high-water mark)
+int disco_ensure_smem(disco_handle* h, const void* func, int bytes);
+
+// Every entry point runs on the handle's device whatever the caller's current device is (the reference CLI wraps the
+// model in DataParallel when several GPUs are visible, so one process may drive several handles).
+struct DiscoDeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DiscoDeviceGuard(const disco_handle* h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) changed = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~DiscoDeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
 
 #define DISCO_CHECK_ARG(cond, ...)                 \
   do {                                             \
@@ -70,3 +87,4 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 bool conv_tc_supported(const disco_conv_desc* d);
+void conv_tc_cache_clear(disco_handle* h);   // frees the cached plans of h->device (caller holds the device guard)

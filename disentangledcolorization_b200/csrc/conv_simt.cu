@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams P) {
         for (int c = 0; c < 9; ++c) { e[c] = expf(Cs[p][c] - m); s += e[c]; }
         for (int c = 0; c < 9; ++c) out[base + c * plane] = e[c] / s;
       } else {
-        for (int c = 0; c < 2; ++c) out[base + c * plane] = tanhf(Cs[p][c]);
+        for (int c = 0; c < 2; ++c) out[base + c * plane] = d.head == DISCO_HEAD_TANH2 ? tanhf(Cs[p][c]) : Cs[p][c];
       }
     }
   }

@@ -643,8 +643,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
           for (int j = 0; j < 9; ++j) outp[base + j * plane] = v[j] * inv;
         } else {
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            outp[base + j * plane] = tanhf(__uint_as_float(r[j]) + (CP ? P.epi_c[0][j] : lds32(wp + 4 * j)));
+          for (int j = 0; j < 2; ++j) {
+            const float y = __uint_as_float(r[j]) + (CP ? P.epi_c[0][j] : lds32(wp + 4 * j));
+            outp[base + j * plane] = phead == DISCO_HEAD_TANH2 ? tanhf(y) : y;      // DISCO_HEAD_RAW2: pre-tanh map
+          }
         }
       }
     }
@@ -1596,11 +1598,12 @@ struct Cached {
   TcParams params;
   Plan plan;
   int grid;
+  int device = -1;
   void* tables_dev = nullptr;
 };
+constexpr size_t kMaxCachedPlans = 2048;   // ~70 descriptors per (batch, H, W) workspace of one forward
 std::mutex g_mu;
 std::map<std::string, Cached> g_cache;
-int32_t* g_error_flag = nullptr;
 long long* g_dbg = nullptr;
 
 bool g_allow_pdl = true;
@@ -1634,96 +1637,80 @@ int launch_tc(Kern kern, const TcParams& P, int grid, int threads, size_t smem, 
 }
 
 template <int BN, int KC, int MT>
-int launch_cfg(const TcParams& P, int grid, cudaStream_t st) {
+int launch_cfg(disco_handle* h, const TcParams& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, KC, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = disco_ensure_smem(h, (const void*)conv_tc_kernel<BN, KC, MT, false>, C::SMEM_BYTES)) return rc;
   return launch_tc(conv_tc_kernel<BN, KC, MT, false>, P, grid, kThreads, C::SMEM_BYTES, 1, st);
 }
 
 // CTA-pair variant: clusters of two CTAs (one TPC), `grid` is even
 template <int BN, int KC, int MT>
-int launch_pair_cfg(const TcParams& P, int grid, cudaStream_t st) {
+int launch_pair_cfg(disco_handle* h, const TcParams& P, int grid, cudaStream_t st) {
   using C = Cfg<BN, KC, MT, true>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = disco_ensure_smem(h, (const void*)conv_tc_kernel<BN, KC, MT, true>, C::SMEM_BYTES)) return rc;
   return launch_tc(conv_tc_kernel<BN, KC, MT, true>, P, grid, kThreads, C::SMEM_BYTES, 2, st);
 }
 
 template <int BN, int KC, bool CP, bool PAIR>
-int launch_res_cfg2(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_res_kernel<BN, KC, CP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+int launch_res_cfg2(disco_handle* h, const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+  if (int rc = disco_ensure_smem(h, (const void*)conv_tc_res_kernel<BN, KC, CP, PAIR>, smem_bytes)) return rc;
   return launch_tc(conv_tc_res_kernel<BN, KC, CP, PAIR>, P, grid, kThreadsRes, (size_t)smem_bytes, PAIR ? 2 : 1, st);
 }
 template <int BN, int KC>
-int launch_res_cfg(const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
+int launch_res_cfg(disco_handle* h, const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
   if constexpr (BN == 64) {
     if (pair)
-      return P.const_params ? launch_res_cfg2<BN, KC, true, true>(P, grid, smem_bytes, st)
-                            : launch_res_cfg2<BN, KC, false, true>(P, grid, smem_bytes, st);
+      return P.const_params ? launch_res_cfg2<BN, KC, true, true>(h, P, grid, smem_bytes, st)
+                            : launch_res_cfg2<BN, KC, false, true>(h, P, grid, smem_bytes, st);
   }
-  return P.const_params ? launch_res_cfg2<BN, KC, true, false>(P, grid, smem_bytes, st)
-                        : launch_res_cfg2<BN, KC, false, false>(P, grid, smem_bytes, st);
+  return P.const_params ? launch_res_cfg2<BN, KC, true, false>(h, P, grid, smem_bytes, st)
+                        : launch_res_cfg2<BN, KC, false, false>(h, P, grid, smem_bytes, st);
 }
 
 template <int BN, int KC, int MT, bool PAIR>
-int launch_grp_cfg(const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    DISCO_CUDA(cudaFuncSetAttribute(conv_tc_grp_kernel<BN, KC, MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_bytes = smem_bytes;
-  }
+int launch_grp_cfg(disco_handle* h, const TcParams& P, int grid, int smem_bytes, cudaStream_t st) {
+  if (int rc = disco_ensure_smem(h, (const void*)conv_tc_grp_kernel<BN, KC, MT, PAIR>, smem_bytes)) return rc;
   return launch_tc(conv_tc_grp_kernel<BN, KC, MT, PAIR>, P, grid, kThreads, (size_t)smem_bytes, PAIR ? 2 : 1, st);
 }
 
-int launch_grp(const Plan& pl, const TcParams& P, int grid, cudaStream_t st) {
+int launch_grp(disco_handle* h, const Plan& pl, const TcParams& P, int grid, cudaStream_t st) {
   if (pl.BN == 256 && pl.MT == 1)
-    return pl.pair ? launch_grp_cfg<256, 64, 1, true>(P, grid, pl.grp_smem_bytes, st)
-                   : launch_grp_cfg<256, 64, 1, false>(P, grid, pl.grp_smem_bytes, st);
+    return pl.pair ? launch_grp_cfg<256, 64, 1, true>(h, P, grid, pl.grp_smem_bytes, st)
+                   : launch_grp_cfg<256, 64, 1, false>(h, P, grid, pl.grp_smem_bytes, st);
   if (pl.BN == 128 && pl.MT == 2)
-    return pl.pair ? launch_grp_cfg<128, 64, 2, true>(P, grid, pl.grp_smem_bytes, st)
-                   : launch_grp_cfg<128, 64, 2, false>(P, grid, pl.grp_smem_bytes, st);
+    return pl.pair ? launch_grp_cfg<128, 64, 2, true>(h, P, grid, pl.grp_smem_bytes, st)
+                   : launch_grp_cfg<128, 64, 2, false>(h, P, grid, pl.grp_smem_bytes, st);
   disco_set_error("conv_tc: unsupported grouped configuration BN %d MT %d", pl.BN, pl.MT);
   return DISCO_ERR_INVALID;
 }
 
 template <int KC>
-int launch_res_bn(int BN, const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
+int launch_res_bn(disco_handle* h, int BN, const TcParams& P, int grid, int smem_bytes, bool pair, cudaStream_t st) {
   switch (BN) {
-    case 16: return launch_res_cfg<16, KC>(P, grid, smem_bytes, pair, st);
-    case 32: return launch_res_cfg<32, KC>(P, grid, smem_bytes, pair, st);
-    case 64: return launch_res_cfg<64, KC>(P, grid, smem_bytes, pair, st);
+    case 16: return launch_res_cfg<16, KC>(h, P, grid, smem_bytes, pair, st);
+    case 32: return launch_res_cfg<32, KC>(h, P, grid, smem_bytes, pair, st);
+    case 64: return launch_res_cfg<64, KC>(h, P, grid, smem_bytes, pair, st);
   }
   disco_set_error("conv_tc: unsupported resident BN %d", BN);
   return DISCO_ERR_INVALID;
 }
 
 template <int KC>
-int launch_bn(int BN, int MT, const TcParams& P, int grid, cudaStream_t st) {
+int launch_bn(disco_handle* h, int BN, int MT, const TcParams& P, int grid, cudaStream_t st) {
   if (MT == 2) {
     switch (BN) {
-      case 16: return launch_cfg<16, KC, 2>(P, grid, st);
-      case 32: return launch_cfg<32, KC, 2>(P, grid, st);
-      case 64: return launch_cfg<64, KC, 2>(P, grid, st);
-      case 128: return launch_cfg<128, KC, 2>(P, grid, st);
+      case 16: return launch_cfg<16, KC, 2>(h, P, grid, st);
+      case 32: return launch_cfg<32, KC, 2>(h, P, grid, st);
+      case 64: return launch_cfg<64, KC, 2>(h, P, grid, st);
+      case 128: return launch_cfg<128, KC, 2>(h, P, grid, st);
     }
   } else {
     switch (BN) {
-      case 16: return launch_cfg<16, KC, 1>(P, grid, st);
-      case 32: return launch_cfg<32, KC, 1>(P, grid, st);
-      case 64: return launch_cfg<64, KC, 1>(P, grid, st);
-      case 128: return launch_cfg<128, KC, 1>(P, grid, st);
-      case 256: return launch_cfg<256, KC, 1>(P, grid, st);
+      case 16: return launch_cfg<16, KC, 1>(h, P, grid, st);
+      case 32: return launch_cfg<32, KC, 1>(h, P, grid, st);
+      case 64: return launch_cfg<64, KC, 1>(h, P, grid, st);
+      case 128: return launch_cfg<128, KC, 1>(h, P, grid, st);
+      case 256: return launch_cfg<256, KC, 1>(h, P, grid, st);
     }
   }
   disco_set_error("conv_tc: unsupported BN %d / MT %d", BN, MT);
@@ -1733,6 +1720,25 @@ int launch_bn(int BN, int MT, const TcParams& P, int grid, cudaStream_t st) {
 }  // namespace
 
 bool conv_tc_supported(const disco_conv_desc* d) { return build_plan(d).ok; }
+
+void conv_tc_cache_clear(disco_handle* h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto it = g_cache.begin(); it != g_cache.end();) {
+    if (it->second.device == h->device) {
+      cudaFree(it->second.tables_dev);         // synchronises the device
+      it = g_cache.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+extern "C" int disco_conv_tc_cache_clear(disco_handle* h) {
+  DISCO_CHECK_ARG(h != nullptr, "conv_tc_cache_clear: null handle");
+  DiscoDeviceGuard guard(h);
+  conv_tc_cache_clear(h);
+  return DISCO_OK;
+}
 
 extern "C" int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d) {
   return h && d && h->use_tc && build_plan(d).ok ? 1 : 0;
@@ -1812,24 +1818,27 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   std::string key(reinterpret_cast<const char*>(d), sizeof(*d));
   key.append(reinterpret_cast<const char*>(&h->device), sizeof(int));
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_cache.size() > 8192) {
-    cudaStreamSynchronize(st);
-    for (auto& kv : g_cache) cudaFree(kv.second.tables_dev);
+  if (g_cache.size() > kMaxCachedPlans) {
+    // plans of other devices are freed on their own device
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_cache) {
+      if (kv.second.device != cur) cudaSetDevice(kv.second.device), cur = kv.second.device;
+      cudaFree(kv.second.tables_dev);          // cudaFree synchronises: no launch still reads the tables
+    }
+    if (cur != h->device) cudaSetDevice(h->device);
     g_cache.clear();
   }
   auto it = g_cache.find(key);
   if (it == g_cache.end()) {
     Cached c;
+    c.device = h->device;
     c.plan = build_plan(d);
     DISCO_CHECK_ARG(c.plan.ok, "conv_tc: descriptor not supported");
     const Plan& pl = c.plan;
     TcParams& P = c.params;
     memset(&P, 0, sizeof(P));
-    if (!g_error_flag) {
-      DISCO_CUDA(cudaMalloc(&g_error_flag, sizeof(int32_t)));
-      DISCO_CUDA(cudaMemset(g_error_flag, 0, sizeof(int32_t)));
-    }
-    P.error_flag = g_error_flag;
+    P.error_flag = h->error_flag;
     if (getenv("DISCO_TC_MODE")) P.dbg_mode = atoi(getenv("DISCO_TC_MODE"));
     {
       // bit 0: resident kernel, bit 1: streaming kernels
@@ -1937,21 +1946,21 @@ int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   int rc;
   if (c.plan.resident) {
     switch (c.plan.KC) {
-      case 64: rc = launch_res_bn<64>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
-      case 32: rc = launch_res_bn<32>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
-      case 16: rc = launch_res_bn<16>(c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
+      case 64: rc = launch_res_bn<64>(h, c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
+      case 32: rc = launch_res_bn<32>(h, c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
+      case 16: rc = launch_res_bn<16>(h, c.plan.BN, c.params, c.grid, c.plan.res_smem_bytes, c.plan.pair, st); break;
       default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
     }
   } else if (c.plan.grouped) {
-    rc = launch_grp(c.plan, c.params, c.grid, st);
+    rc = launch_grp(h, c.plan, c.params, c.grid, st);
   } else if (c.plan.pair) {
-    if (c.plan.BN == 256) rc = launch_pair_cfg<256, 64, 1>(c.params, c.grid, st);
-    else rc = launch_pair_cfg<128, 64, 2>(c.params, c.grid, st);
+    if (c.plan.BN == 256) rc = launch_pair_cfg<256, 64, 1>(h, c.params, c.grid, st);
+    else rc = launch_pair_cfg<128, 64, 2>(h, c.params, c.grid, st);
   } else {
     switch (c.plan.KC) {
-      case 64: rc = launch_bn<64>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
-      case 32: rc = launch_bn<32>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
-      case 16: rc = launch_bn<16>(c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
+      case 64: rc = launch_bn<64>(h, c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
+      case 32: rc = launch_bn<32>(h, c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
+      case 16: rc = launch_bn<16>(h, c.plan.BN, c.plan.MT, c.params, c.grid, st); break;
       default: disco_set_error("conv_tc: bad KC"); return DISCO_ERR_INVALID;
     }
   }

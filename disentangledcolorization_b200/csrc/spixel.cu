@@ -203,6 +203,7 @@ extern "C" int disco_poolfeat(disco_handle* h, int dtype, const void* feats, con
   DISCO_CHECK_ARG(h && feats && affinity && partial && tokens && spix_ab && conf && sizes, "poolfeat: null pointer");
   DISCO_CHECK_ARG(C == 64, "poolfeat: C must be 64 (got %d)", C);
   DISCO_CHECK_ARG(H > 0 && W > 0 && H % SP == 0 && W % SP == 0, "poolfeat: H, W must be multiples of 16 (got %dx%d)", H, W);
+  DiscoDeviceGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(W / SP, H / SP, batch);
   if (dtype == DISCO_F32)
@@ -220,6 +221,7 @@ extern "C" int disco_upfeat(disco_handle* h, int dtype, const float* tokens, con
   DISCO_CHECK_ARG(h && tokens && affinity && out, "upfeat: null pointer");
   DISCO_CHECK_ARG(C == 64, "upfeat: C must be 64 (got %d)", C);
   DISCO_CHECK_ARG(H > 0 && W > 0 && H % SP == 0 && W % SP == 0, "upfeat: H, W must be multiples of 16 (got %dx%d)", H, W);
+  DiscoDeviceGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(W / SP, H / SP, batch);
   if (dtype == DISCO_F32)

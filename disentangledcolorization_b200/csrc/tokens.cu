@@ -714,6 +714,7 @@ extern "C" int disco_linear(disco_handle* h, const disco_linear_desc* d, void* s
   DISCO_CHECK_ARG(!d->ln_gamma || d->N == 64, "linear: LayerNorm epilogue needs N == 64");
   DISCO_CHECK_ARG(!d->pos || (d->S > 0 && d->pos_cols % 64 == 0), "linear: pos needs S > 0 and pos_cols %% 64 == 0");
   DISCO_CHECK_ARG(!d->hint_mask || (d->labels && d->emb), "linear: hint embedding needs labels and emb");
+  DiscoDeviceGuard guard(h);
   dim3 grid((d->M + LT - 1) / LT, (d->N + LT - 1) / LT);
   linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
   DISCO_LAUNCH_CHECK(h);
@@ -727,11 +728,8 @@ extern "C" int disco_encoder_tail(disco_handle* h, const float* att, const float
                   "encoder_tail: bad argument");
   const EncTailArgs a{att, x, y, M, wo, bo, ln1_g, ln1_b, w1, b1, w2, b2, ln2_g, ln2_b};
   const int smem = ((64 + 256 + 32) * 68 + 64 * 65) * (int)sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    DISCO_CUDA(cudaFuncSetAttribute(encoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  DiscoDeviceGuard guard(h);
+  if (int rc = disco_ensure_smem(h, (const void*)encoder_tail_kernel, smem)) return rc;
   encoder_tail_kernel<<<(M + 63) / 64, 256, smem, (cudaStream_t)stream>>>(a);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
@@ -741,8 +739,8 @@ extern "C" int disco_attention(disco_handle* h, const float* qkv, int batch, int
   DISCO_CHECK_ARG(h && qkv && out && batch > 0 && S > 0, "attention: bad argument");
   const size_t smem = (size_t)((S + 3) & ~3) * 16 * sizeof(float);
   DISCO_CHECK_ARG(smem <= 200 * 1024, "attention: S=%d too large for the shared-memory K/V stage", S);
-  if (smem > 48 * 1024)
-    DISCO_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DiscoDeviceGuard guard(h);
+  if (int rc = disco_ensure_smem(h, (const void*)attention_kernel, (int)smem)) return rc;
   // two queries per thread, 128-thread CTAs (measured best of 32/64/128/256 at both S = 256 and S = 1024: enough CTAs
   // for an even spread over the SMs, K/V stage shared by 256 queries)
   int threads = 128;
@@ -760,6 +758,7 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   DISCO_CHECK_ARG(K >= 1 && K <= KMAX, "kmeans: K must be in [1,%d] (got %d)", KMAX, K);
   DISCO_CHECK_ARG(K <= S, "kmeans: n_clusters (%d) exceeds the number of tokens (%d)", K, S);
   KmArgs a{X, init_idx, draws, n_draws, sizes, batch, S, K, iter_limit, tol, assign, hint_mask, events, iters};
+  DiscoDeviceGuard guard(h);
   cudaStream_t st = (cudaStream_t)stream;
   DISCO_CUDA(cudaMemsetAsync(events, 0, sizeof(int32_t) * (batch + 2), st));
   // dynamic smem: [XT (64 x (S+1) floats) when it fits] + assign[S] + members[S]
@@ -767,8 +766,7 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
   const int use_smem = dyn_full <= 160 * 1024;
   const size_t dyn = use_smem ? dyn_full : 2 * (size_t)S * sizeof(int);
   DISCO_CHECK_ARG(dyn <= 160 * 1024, "kmeans: S=%d too large", S);
-  if (dyn > 32 * 1024)
-    DISCO_CUDA(cudaFuncSetAttribute(kmeans_anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  if (int rc = disco_ensure_smem(h, (const void*)kmeans_anchor_kernel, (int)dyn)) return rc;
   kmeans_anchor_kernel<<<batch, 512, dyn, st>>>(a, 0, use_smem);
   DISCO_LAUNCH_CHECK(h);
   kmeans_anchor_kernel<<<1, 512, dyn, st>>>(a, 1, use_smem);
@@ -779,6 +777,7 @@ extern "C" int disco_kmeans_anchor(disco_handle* h, const float* X, const int32_
 extern "C" int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
                                    int32_t* labels3, float* colors3, void* stream) {
   DISCO_CHECK_ARG(h && logits && q_to_ab && labels3 && colors3, "token_sample3: null pointer");
+  DiscoDeviceGuard guard(h);
   token_sample3_kernel<<<(batch * S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(logits, q_to_ab, batch, S, labels3, colors3);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
@@ -788,6 +787,7 @@ extern "C" int disco_token_labels(disco_handle* h, int mode, const float* src, c
                                   int32_t* labels, float* colors, void* stream) {
   DISCO_CHECK_ARG(h && src && q_to_ab && labels, "token_labels: null pointer");
   DISCO_CHECK_ARG(mode == 0 || mode == 1, "token_labels: mode must be 0 or 1");
+  DiscoDeviceGuard guard(h);
   token_labels_kernel<<<(batch * S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mode, src, q_to_ab, batch, S, labels, colors);
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;

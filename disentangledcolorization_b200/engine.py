@@ -9,6 +9,7 @@ Responsibilities (plumbing only -- all arithmetic on the path runs in libdisco_b
     image in batch order (clusterkit.py:107) and one `torch.randint(S, (1,))` per empty cluster
     (clusterkit.py:182).
 """
+import collections
 import ctypes as C
 import math
 
@@ -20,7 +21,7 @@ from .cielab import Q_TO_AB
 
 _DT = {"fp32": (_lib.F32, torch.float32), "bf16": (_lib.BF16, torch.bfloat16)}
 _ACT = {"none": _lib.ACT_NONE, "relu": _lib.ACT_RELU, "lrelu": _lib.ACT_LRELU}
-_HEAD = {None: _lib.HEAD_NONE, "softmax9": _lib.HEAD_SOFTMAX9, "tanh2": _lib.HEAD_TANH2}
+_HEAD = {None: _lib.HEAD_NONE, "softmax9": _lib.HEAD_SOFTMAX9, "tanh2": _lib.HEAD_TANH2, "raw2": _lib.HEAD_RAW2}
 N_DRAWS = 4096
 
 
@@ -90,7 +91,11 @@ class Engine:
         self.n_clusters = n_clusters
         self.enhanced = enhanced
         self.random_hint = random_hint
-        self._ws = {}
+        # activation workspaces, least recently used first; bounded (the CLI's --no_resize mode feeds a new
+        # image size per file and every (batch, H, W) owns ~9 GB at batch 64)
+        self._ws = collections.OrderedDict()
+        self.max_workspaces = 4
+        self.max_workspace_bytes = 64 << 30
         self._pos = {}
         self._pending_rng = None
         self._prof = None
@@ -160,6 +165,7 @@ class Engine:
         key = (B, H, W)
         ws = self._ws.get(key)
         if ws is not None:
+            self._ws.move_to_end(key)
             return ws
         if H % 16 or W % 16 or H <= 0 or W <= 0:
             raise _lib.DiscoError(f"H and W must be positive multiples of 16 (got {H}x{W}); the reference has the "
@@ -179,7 +185,7 @@ class Engine:
                 Ho, Wo = H // op.scale, W // op.scale
                 if op.head == "softmax9":
                     out = torch.empty(B, 9, Ho, Wo, **f32)
-                elif op.head == "tanh2":
+                elif op.head in ("tanh2", "raw2"):
                     out = torch.empty(B, 2, Ho, Wo, **f32)
                 else:
                     out = torch.empty(B, Ho, Wo, op.cout, dtype=self.dt_torch, device=dev)
@@ -205,9 +211,32 @@ class Engine:
                    events_host=torch.zeros(B + 2, dtype=torch.int32).pin_memory())
         if (h, w) not in self._pos:
             self._pos[(h, w)] = position_table(h, w, dev)
-        ws = dict(bufs=bufs, plans=plans, tok=tok, h=h, w=w, S=S, descs={})
+        nbytes = sum(t.numel() * t.element_size() for t in list(bufs.values()) + list(tok.values()) if t.is_cuda)
+        ws = dict(bufs=bufs, plans=plans, tok=tok, h=h, w=w, S=S, descs={}, nbytes=nbytes)
         self._ws[key] = ws
+        self._evict(keep=key)
         return ws
+
+    def _evict(self, keep):
+        """Drops least-recently-used workspaces beyond `max_workspaces` / `max_workspace_bytes`, together with their CUDA
+        graphs and the library's launch plans (which hold the dead buffers' addresses).  The two most recent workspaces
+        always stay (--diverse uses the batch-1 and the batch-3 workspace in one forward)."""
+        def over():
+            return (len(self._ws) > self.max_workspaces
+                    or sum(w["nbytes"] for w in self._ws.values()) > self.max_workspace_bytes)
+        dropped = False
+        while len(self._ws) > 2 and over():
+            old = next(iter(self._ws))
+            if old == keep:
+                break
+            del self._ws[old]
+            self._graphs.pop(old, None)
+            dropped = True
+        if dropped:
+            torch.cuda.synchronize(self.device)      # nothing in flight still reads the freed buffers
+            _lib.check(self.lib.disco_conv_tc_cache_clear(self.handle.h), "disco_conv_tc_cache_clear")
+            for w in self._ws.values():              # surviving descriptors are rebuilt lazily (their plans were dropped too)
+                w["descs"] = {}
 
     def _conv_desc(self, ws, pc, Ho, Wo, B, bufs):
         op = pc.op
@@ -322,27 +351,32 @@ class Engine:
         if int(events_host[-1]) != 0:
             raise _lib.DiscoError("k-means consumed more than %d empty-cluster draws" % N_DRAWS)
         used = int(events_host[-2])
-        torch.set_rng_state(state)
         if used:
+            # the draws are taken from the generator as it stood when the forward was issued; if the caller has drawn from
+            # torch's CPU generator since then (only possible with lazy_rng), rewinding it would silently replay their
+            # numbers -- refuse instead
+            if not torch.equal(torch.get_rng_state(), state):
+                raise _lib.DiscoError("lazy_rng: torch's CPU generator was used between a forward that consumed empty-cluster "
+                                      "draws and its sync_rng(); call engine.sync_rng() right after the forward")
             torch.randint(S, (used,))
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, gray, ab, sampled_T=0, hint_mask=None, sync_rng=True, init_idx=None):
         """Returns the reference 6-tuple (pal_logit, ref_logit, pred_colors, affinity_map, spix_colors, hint_mask)."""
-        if (self.use_graph and self._prof is None and sampled_T == 0 and hint_mask is None and not self.random_hint
-                and gray.dim() == 4 and gray.is_cuda and ab.is_cuda):
-            return self._forward_graph(gray, ab, sync_rng, init_idx)
-        return self._forward_impl(gray, ab, sampled_T, hint_mask, sync_rng, init_idx)
+        with torch.cuda.device(self.device):     # allocations, stream lookup and launches follow the model's device
+            if (self.use_graph and self._prof is None and sampled_T == 0 and hint_mask is None and not self.random_hint
+                    and gray.dim() == 4 and gray.is_cuda and ab.is_cuda):
+                return self._forward_graph(gray, ab, sync_rng, init_idx)
+            return self._forward_impl(gray, ab, sampled_T, hint_mask, sync_rng, init_idx)
 
     def _host_draws(self, tok, B, S, init_idx):
         """Host RNG consumption of one forward (see module docstring); fills the pinned staging buffers."""
         K = self.n_clusters
         if init_idx is not None:                 # sharded runs: rows drawn for the global batch (dist.py)
             tok["init_idx_host"].copy_(torch.as_tensor(np.asarray(init_idx, dtype=np.int32)).view(B, K))
-        else:
-            for n in range(B):
-                tok["init_idx_host"][n] = torch.from_numpy(np.random.choice(S, K, replace=False).astype(np.int32))
+        else:                                    # B x np.random.choice(S, K, replace=False), one native call
+            tok["init_idx_host"].copy_(torch.from_numpy(_lib.choice_rows(S, K, B)))
         state = torch.get_rng_state()
         tok["draws_host"].copy_(torch.randint(S, (N_DRAWS,)).to(torch.int32))
         torch.set_rng_state(state)
@@ -554,3 +588,8 @@ class Engine:
 
     def kmeans_iterations(self, B, H, W):
         return self._ws[(B, H, W)]["tok"]["iters"].cpu()
+
+    def kmeans_draws(self, B, H, W):
+        """Empty-cluster draws the last k-means of this shape consumed (total over the batch)."""
+        torch.cuda.synchronize(self.device)
+        return int(self._ws[(B, H, W)]["tok"]["events"][B].item())

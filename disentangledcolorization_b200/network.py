@@ -126,6 +126,11 @@ class _ConvNet(nn.Module):
             _lib.check(handle.lib.disco_conv(handle.h, C.byref(d), stream), "disco_conv")
         return bufs[out_name]
 
+    def _run_on(self, inputs, out_name):
+        """`_run` with the input's device made current (kernels, allocations and the stream lookup all follow it)."""
+        with torch.cuda.device(inputs["gray"].device):
+            return self._run(inputs, out_name)
+
 
 class SpixelNet(_ConvNet):
     """reference models/network.py:260-313: (N,1,H,W) -> (N,9,H,W) soft 9-neighbour assignment."""
@@ -146,7 +151,7 @@ class SpixelNet(_ConvNet):
 
     @torch.no_grad()
     def forward(self, x):
-        return self._run({"gray": x.float().contiguous()}, "affinity")
+        return self._run_on({"gray": x.float().contiguous()}, "affinity")
 
 
 class ColorProbNet(_ConvNet):
@@ -168,13 +173,14 @@ class ColorProbNet(_ConvNet):
 
     @torch.no_grad()
     def forward(self, input_grays):
-        out = self._run({"gray": input_grays.float().contiguous()}, "pred_feats")
+        out = self._run_on({"gray": input_grays.float().contiguous()}, "pred_feats")
         return out.permute(0, 3, 1, 2).float().contiguous()
 
 
 class HourGlass2(_ConvNet):
-    """reference models/network.py:125-144 with inChannel=65, outChannel=2: (N,65,H,W) -> (N,2,H,W)
-    (pre-tanh in the reference; here `apply_tanh` selects whether the fused tanh head output is undone)."""
+    """reference models/network.py:125-144 with inChannel=65, outChannel=2: (N,65,H,W) -> (N,2,H,W), the pre-tanh map
+    exactly as the reference's `HourGlass2.forward` returns it (the tanh belongs to `AnchorColorProb.forward`,
+    models/model.py:197, where it is fused into the same conv's epilogue as the `tanh2` head)."""
     _PREFIX, _NET = "enhanceNet.", "enhanceNet"
 
     def __init__(self, inChannel=3, outChannel=1, resNum=3, normLayer=None):
@@ -188,12 +194,14 @@ class HourGlass2(_ConvNet):
         _init_from_synth(self, self._PREFIX)
 
     def _ops(self):
-        return netspec.enhancenet_ops()
+        ops = netspec.enhancenet_ops()
+        assert ops[-1].head == "tanh2"
+        ops[-1].head = "raw2"            # standalone: no tanh (DISCO_HEAD_RAW2)
+        return ops
 
     @torch.no_grad()
     def forward(self, x):
         from .engine import _DT
         gray = x[:, :1].float().contiguous()
         feats = x[:, 1:].permute(0, 2, 3, 1).contiguous().to(_DT[self.precision][1])
-        y = self._run({"gray": gray, "full_feats": feats}, "pred_colors")      # tanh(outConv(.))
-        return torch.atanh(y.clamp(-1 + 1e-7, 1 - 1e-7))                        # reference returns pre-tanh
+        return self._run_on({"gray": gray, "full_feats": feats}, "pred_colors")

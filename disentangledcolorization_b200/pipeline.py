@@ -15,6 +15,7 @@ class ColorizePipeline:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth = depth
         self.sampled_T = sampled_T
+        self.forward_kwargs = None       # optional callable -> extra keyword arguments of each forward (e.g. init_idx of a shard)
         self.h2d = torch.cuda.Stream(self.dev)
         self.d2h = torch.cuda.Stream(self.dev)
         self.slots = []
@@ -36,26 +37,48 @@ class ColorizePipeline:
             s["ab"].copy_(ab_host, non_blocking=True)
             s["ev_in"].record(self.h2d)
 
-    def run(self, batches, on_step=None, before_step=None):
-        """batches: sequence of (gray_host, ab_host) pinned fp32 tensors.  Returns the list of pinned host tensors that
-        received pred_colors of each step (slot buffers: valid until `depth` steps later).  `on_step(out_tuple)` runs on
-        the compute stream right after each forward (e.g. the all-gather of the multi-GPU job)."""
+    def run(self, batches, on_step=None, before_step=None, on_result=None, keep="copy"):
+        """batches: sequence of (gray_host, ab_host) pinned fp32 tensors.  `on_step(out_tuple)` runs on the compute
+        stream right after each forward (e.g. the all-gather of the multi-GPU job).
+
+        Results: `on_result(i, host_tensor)` (when given) is called for every step as soon as its D2H copy has landed,
+        while the slot buffer is still that step's.  The returned list holds one pinned host tensor per step:
+        keep="copy" (default) hands out private copies; keep="alias" returns the `depth` slot buffers themselves, each
+        valid only until `depth` steps later (zero-copy, for callers that consume results through `on_result`)."""
+        if keep not in ("copy", "alias"):
+            raise ValueError("keep must be 'copy' or 'alias'")
         main = torch.cuda.current_stream(self.dev)
         n = len(batches)
-        results = []
+        results = [None] * n
         if n == 0:
             return results
+        static_out = bool(getattr(self.model, "use_cuda_graph", False) and getattr(self.model, "graph_static_outputs", False))
+        last_out_ev = None
+
+        def retire(j):
+            """Step j's D2H is complete (waits for it): deliver / copy its result before the slot is reused."""
+            sj = self.slots[j % self.depth]
+            sj["ev_out"].synchronize()
+            if on_result is not None:
+                on_result(j, sj["out_host"])
+            results[j] = sj["out_host"].clone() if keep == "copy" else sj["out_host"]
+
         self._stage(0, *batches[0])
         for i in range(n):
             s = self.slots[i % self.depth]
             if i + 1 < n:
                 self._stage((i + 1) % self.depth, *batches[i + 1])
+            if i >= self.depth:
+                retire(i - self.depth)                  # the slot's previous result leaves before it is overwritten
             main.wait_event(s["ev_in"])
-            if s["used"]:
-                main.wait_event(s["ev_out"])            # (no-op in practice) previous D2H out of this slot is done
+            if static_out and last_out_ev is not None:
+                # graph mode with static outputs: pred_colors lives in ONE graph-owned buffer that the next replay
+                # overwrites, so the forward must not start before the previous step's D2H has read it
+                main.wait_event(last_out_ev)
             if before_step is not None:
                 before_step()
-            out = self.model(s["gray"], s["ab"], True, self.sampled_T)
+            kw = self.forward_kwargs() if self.forward_kwargs is not None else {}
+            out = self.model(s["gray"], s["ab"], True, self.sampled_T, **kw)
             if on_step is not None:
                 on_step(out)
             s["ev_compute"].record(main)
@@ -64,8 +87,11 @@ class ColorizePipeline:
             with torch.cuda.stream(self.d2h):
                 s["out_host"].copy_(out[2], non_blocking=True)
                 s["ev_out"].record(self.d2h)
-            out[2].record_stream(self.d2h)
-            results.append(s["out_host"])
+            last_out_ev = s["ev_out"]
+            if not static_out:
+                out[2].record_stream(self.d2h)
+        for j in range(max(0, n - self.depth), n):
+            retire(j)
         self.d2h.synchronize()
         main.synchronize()
         return results

@@ -37,7 +37,9 @@ enum disco_status {
 
 enum disco_dtype { DISCO_F32 = 0, DISCO_BF16 = 1 };
 enum disco_act { DISCO_ACT_NONE = 0, DISCO_ACT_RELU = 1, DISCO_ACT_LRELU = 2 };
-enum disco_head { DISCO_HEAD_NONE = 0, DISCO_HEAD_SOFTMAX9 = 1, DISCO_HEAD_TANH2 = 2 };
+/* heads write fp32 NCHW: softmax over 9 channels, tanh of 2 channels, or the 2 raw channels (HourGlass2.forward
+ * standalone returns the pre-tanh map, models/network.py:134,144) */
+enum disco_head { DISCO_HEAD_NONE = 0, DISCO_HEAD_SOFTMAX9 = 1, DISCO_HEAD_TANH2 = 2, DISCO_HEAD_RAW2 = 3 };
 enum disco_conv_kind { DISCO_CONV3 = 0, DISCO_DECONV4 = 1 };
 
 int disco_version(void);
@@ -116,6 +118,10 @@ int disco_set_tensor_core(disco_handle* h, int enable);
 int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d);
 int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d);
 int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float* w_f32_host, uint16_t* w_bf16_host);
+/* Drops the cached launch plans (tensor maps, tap tables) of this handle's device.  The cache is keyed on the whole
+ * descriptor, pointers included; a host executor that frees an activation workspace calls this so that plans of dead
+ * buffers do not accumulate (the CLI's --no_resize mode sees a new image size per file).  Synchronises the device. */
+int disco_conv_tc_cache_clear(disco_handle* h);
 /* debug aid: per-role clock64 timeline of CTA 0 of the last tensor-core launch made with DISCO_TC_DEBUG=1 */
 int disco_debug_timeline(long long* out_host);
 
@@ -207,6 +213,19 @@ int disco_token_labels(disco_handle* h, int mode, const float* src, const float*
  *   colors3 fp32 [3][B,2,S] = q_to_ab[pick]/110 */
 int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
                         int32_t* labels3, float* colors3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host helper (no device work): the k-means initialisation draws of clusterkit.initialize
+ * (models/clusterkit.py:99-109), `np.random.choice(S, K, replace=False)` once per image in batch order, for `rows`
+ * images in one call.  Bit-identical to numpy's legacy global RandomState: choice(replace=False) is
+ * permutation(S)[:K], a Fisher-Yates shuffle of arange(S) from the top index down whose j = random_interval(i) is a
+ * masked, rejection-sampled 32-bit MT19937 output.  The caller passes the generator state it read with
+ * np.random.get_state() (key[624], pos) and writes the updated state back with np.random.set_state(), so numpy's stream
+ * ends exactly where `rows` calls of np.random.choice would have left it.  Rows in [keep_lo, keep_hi) are written to
+ * out[(keep_hi-keep_lo)*K] (a rank of a sharded job walks the whole global batch but keeps its slice).
+ * 16 us -> ~1 us of host time per image: at 8 ranks x 64 images the python loop was on the critical path. */
+int disco_host_choice_rows(uint32_t* mt_key, int32_t* mt_pos, int S, int K, int rows, int keep_lo, int keep_hi,
+                           int32_t* out);
 
 #ifdef __cplusplus
 }

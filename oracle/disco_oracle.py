@@ -20,6 +20,7 @@ Structure is deliberately independent of disentangledcolorization_b200/netspec.p
 fusion: conv -> activation -> BN exactly in the reference's order) so that it also checks the
 product's weight folding.
 """
+import contextlib
 import math
 
 import numpy as np
@@ -27,6 +28,30 @@ import torch
 import torch.nn.functional as F
 
 N_VOCAB = 313
+
+# ----------------------------------------------------------------------------------------------
+# bf16-storage emulation (tolerance derivation only; the parity oracle proper is the fp32 path)
+# ----------------------------------------------------------------------------------------------
+# With `emulate_bf16()` active, conv weights and every activation map a bf16 pipeline would keep in
+# memory between two convolutions are rounded to bf16 (round-to-nearest-even) while all arithmetic
+# stays fp32 -- "torch fp32 vs torch with bf16 storage" on the reference's own formulation.  The
+# distance between the two is the error ANY bf16-storage implementation of this network carries;
+# oracle/derive_bf16_tolerance.py measures it and tests/ gate the CUDA bf16 path at 1.5x that.
+_EMU = False
+
+
+@contextlib.contextmanager
+def emulate_bf16(on=True):
+    global _EMU
+    prev, _EMU = _EMU, bool(on)
+    try:
+        yield
+    finally:
+        _EMU = prev
+
+
+def _q(x):
+    return x.to(torch.bfloat16).to(torch.float32) if _EMU else x
 
 
 # ----------------------------------------------------------------------------------------------
@@ -44,10 +69,10 @@ def _w(sd, key):
     """Eval-mode weight of a (possibly spectral-normalised) conv.  torch spectral_norm in eval:
     sigma = u.(W_mat v); W = weight_orig / sigma (call sites models/network.py:152-185,36)."""
     if key + ".weight" in sd:
-        return sd[key + ".weight"]
+        return _q(sd[key + ".weight"])
     w = sd[key + ".weight_orig"]
     sigma = torch.dot(sd[key + ".weight_u"], torch.mv(w.reshape(w.shape[0], -1), sd[key + ".weight_v"]))
-    return w / sigma
+    return _q(w / sigma)
 
 
 def _conv(sd, key, x, stride=1):
@@ -62,12 +87,12 @@ def _bn(sd, key, x):
 def spixelnet(sd, gray, prefix="segnet.net."):
     """SpixelNet.forward, models/network.py:293-313; conv()/deconv() blocks :240-258."""
     def cbl(name, x, stride=1):
-        y = F.conv2d(x, sd[prefix + name + ".0.weight"], None, stride=stride, padding=1)
-        return F.leaky_relu(_bn(sd, prefix + name + ".1", y), 0.1)
+        y = F.conv2d(x, _q(sd[prefix + name + ".0.weight"]), None, stride=stride, padding=1)
+        return _q(F.leaky_relu(_bn(sd, prefix + name + ".1", y), 0.1))
 
     def dcl(name, x):
-        y = F.conv_transpose2d(x, sd[prefix + name + ".0.weight"], sd[prefix + name + ".0.bias"], stride=2, padding=1)
-        return F.leaky_relu(y, 0.1)
+        y = F.conv_transpose2d(x, _q(sd[prefix + name + ".0.weight"]), sd[prefix + name + ".0.bias"], stride=2, padding=1)
+        return _q(F.leaky_relu(y, 0.1))
 
     o1 = cbl("conv0b", cbl("conv0a", gray))
     o2 = cbl("conv1b", cbl("conv1a", o1, 2))
@@ -78,7 +103,7 @@ def spixelnet(sd, gray, prefix="segnet.net."):
     c2 = cbl("conv2_1", torch.cat((o3, dcl("deconv2", c3)), 1))
     c1 = cbl("conv1_1", torch.cat((o2, dcl("deconv1", c2)), 1))
     c0 = cbl("conv0_1", torch.cat((o1, dcl("deconv0", c1)), 1))
-    mask = F.conv2d(c0, sd[prefix + "pred_mask0.weight"], sd[prefix + "pred_mask0.bias"], padding=1)
+    mask = F.conv2d(c0, _q(sd[prefix + "pred_mask0.weight"]), sd[prefix + "pred_mask0.bias"], padding=1)
     return torch.softmax(mask, dim=1)
 
 
@@ -87,7 +112,9 @@ def colorprobnet(sd, gray, prefix="repnet."):
     def sn_block(name, x, n_convs, first_stride=1):
         for i in range(n_convs):
             x = F.leaky_relu(_conv(sd, f"{prefix}{name}.{2 * i}", x, first_stride if i == 0 else 1), 0.2)
-        return _bn(sd, f"{prefix}{name}.{2 * n_convs}", x)
+            if i + 1 < n_convs:
+                x = _q(x)
+        return _q(_bn(sd, f"{prefix}{name}.{2 * n_convs}", x))
 
     up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
     f1 = sn_block("conv1_2", gray, 2)
@@ -98,34 +125,34 @@ def colorprobnet(sd, gray, prefix="repnet."):
     f6 = sn_block("conv6_3", f5, 3)
     f7 = sn_block("conv7_3", f6, 3)
     f8u = _conv(sd, prefix + "conv8up.1", up(f7)) + _conv(sd, prefix + "conv3short8.0", f3)
-    x = F.relu(f8u)
-    x = F.relu(_conv(sd, prefix + "conv8_3.1", x))
+    x = _q(F.relu(f8u))
+    x = _q(F.relu(_conv(sd, prefix + "conv8_3.1", x)))
     x = F.relu(_conv(sd, prefix + "conv8_3.3", x))
-    f8 = _bn(sd, prefix + "conv8_3.5", x)
-    f9u = _conv(sd, prefix + "conv9up.1", up(f8))
-    f9 = _bn(sd, prefix + "conv9_2.2", F.relu(_conv(sd, prefix + "conv9_2.0", f9u)))
+    f8 = _q(_bn(sd, prefix + "conv8_3.5", x))
+    f9u = _q(_conv(sd, prefix + "conv9up.1", up(f8)))
+    f9 = _q(_bn(sd, prefix + "conv9_2.2", F.relu(_conv(sd, prefix + "conv9_2.0", f9u))))
     f10u = _conv(sd, prefix + "conv10up.1", up(f9))
-    return F.relu(_conv(sd, prefix + "conv10_2.1", F.relu(f10u)))
+    return _q(F.relu(_conv(sd, prefix + "conv10_2.1", _q(F.relu(f10u)))))
 
 
 def hourglass2(sd, x, prefix="enhanceNet.", res_num=3):
     """HourGlass2.forward, models/network.py:136-144; blocks :10-47,66-101."""
     r = lambda k, t, s=1: F.relu(_conv(sd, prefix + k, t, s))
-    f1 = _bn(sd, prefix + "inConv.conv.2", r("inConv.conv.0", r("inConv.inConv.0", x)))
-    f2 = _bn(sd, prefix + "down1.conv.4", r("down1.conv.2", r("down1.conv.0", f1, 2)))
-    f3 = _bn(sd, prefix + "down2.conv.4", r("down2.conv.2", r("down2.conv.0", f2, 2)))
+    f1 = _q(_bn(sd, prefix + "inConv.conv.2", r("inConv.conv.0", _q(r("inConv.inConv.0", x)))))
+    f2 = _q(_bn(sd, prefix + "down1.conv.4", r("down1.conv.2", _q(r("down1.conv.0", f1, 2)))))
+    f3 = _q(_bn(sd, prefix + "down2.conv.4", r("down2.conv.2", _q(r("down2.conv.0", f2, 2)))))
     y = f3
     for i in range(res_num):
-        t = _conv(sd, f"{prefix}residual.{i}.conv.0", y)
-        t = F.relu(_conv(sd, f"{prefix}residual.{i}.conv.1", t))
+        t = _q(_conv(sd, f"{prefix}residual.{i}.conv.0", y))
+        t = _q(F.relu(_conv(sd, f"{prefix}residual.{i}.conv.1", t)))
         t = _conv(sd, f"{prefix}residual.{i}.conv.3", t)
-        y = F.relu(y + t)
+        y = _q(F.relu(y + t))
 
     def upblock(name, t, skip):
-        t = F.interpolate(_conv(sd, f"{prefix}{name}.conv1", t), scale_factor=2, mode="nearest")
-        t = F.relu(_conv(sd, f"{prefix}{name}.combine", torch.cat((t, skip), 1)))
-        t = r(f"{name}.conv2.2", r(f"{name}.conv2.0", t))
-        return _bn(sd, f"{prefix}{name}.conv2.4", t)
+        t = F.interpolate(_q(_conv(sd, f"{prefix}{name}.conv1", t)), scale_factor=2, mode="nearest")
+        t = _q(F.relu(_conv(sd, f"{prefix}{name}.combine", torch.cat((t, skip), 1))))
+        t = r(f"{name}.conv2.2", _q(r(f"{name}.conv2.0", t)))
+        return _q(_bn(sd, f"{prefix}{name}.conv2.4", t))
 
     y = upblock("up2", y, f2)
     y = upblock("up1", y, f1)
@@ -220,7 +247,7 @@ def encoder_stack(sd, stack, x, pos, n_layers=6, n_head=8):
 def encode_ab2ind(ab, neighbours=5, sigma=5.0):
     """ColorLabel.encode_ab2ind (models/basic.py:177-194): soft 5-NN Gaussian code over the 313 bins.
     ab: (N,2,h,w) normalised by 110 -> (N,313,h,w)."""
-    table = q_to_ab()
+    table = q_to_ab().to(ab.device)
     n, _, h, w = ab.shape
     pts = (ab * 110.0).permute(1, 0, 2, 3).reshape(2, -1)                 # (2, m)
     d = torch.cdist(table, pts.t())                                        # (313, m)
@@ -232,13 +259,13 @@ def encode_ab2ind(ab, neighbours=5, sigma=5.0):
     wts = torch.stack(wts)
     wts = wts / wts.sum(0, keepdim=True)
     q = ab.new_zeros(N_VOCAB, pts.shape[1])
-    q[nn_idx, torch.arange(pts.shape[1]).repeat(neighbours, 1)] = wts
+    q[nn_idx, torch.arange(pts.shape[1], device=ab.device).repeat(neighbours, 1)] = wts
     return q.reshape(N_VOCAB, n, h, w).permute(1, 0, 2, 3)
 
 
 def decode_ind2ab(logit, T=0):
     """ColorLabel.decode_ind2ab (models/basic.py:196-218) for integer T: T-th most probable bin."""
-    table = q_to_ab()
+    table = q_to_ab().to(logit.device)
     idx = torch.sort(torch.softmax(logit, dim=1), dim=1, descending=True)[1][:, T]    # (N,h,w)
     return table[idx].permute(0, 3, 1, 2) / 110.0
 
@@ -286,7 +313,7 @@ def anchor_mask(tokens, K, spixel_sizes):
 
 def sample_anchor_colors(prob, T=0, topk=10):
     """AnchorAnalysis._sample_anchor_colors (models/anchor_gen.py:54-90).  prob: (N,313,h,w)."""
-    table = q_to_ab()
+    table = q_to_ab().to(prob.device)
     order = torch.sort(prob, dim=1, descending=True)[1][:, :topk]          # (N,topk,h,w)
     cand = table[order] / 110.0                                           # (N,topk,h,w,2)
     if T == 0:
@@ -320,7 +347,7 @@ def forward(sd, gray, ab, n_clusters=8, sampled_T=0, sp=16, hint_mask=None, stag
     pooled, _ = poolfeat(torch.cat([feats, ab], 1), affinity, sp)          # :114-115
     tokens, spix_colors = pooled[:, :64], pooled[:, 64:]                   # :116-117
     N, C, h, w = tokens.shape
-    pos = position_sine(h, w).unsqueeze(0).expand(N, -1, -1, -1)           # :118
+    pos = position_sine(h, w).to(gray.device).unsqueeze(0).expand(N, -1, -1, -1)           # :118
     sizes = get_spixel_size(affinity, sp)                                  # :121
     src = tokens.flatten(2).transpose(1, 2)                                # (N,S,64)
     pos_seq = pos.flatten(2).transpose(1, 2)
@@ -344,7 +371,7 @@ def forward(sd, gray, ab, n_clusters=8, sampled_T=0, sp=16, hint_mask=None, stag
     hint_seq = F.linear(torch.cat([src, m * onehot, m], 2), sd["trg_word_emb.weight"])   # :185
     dec = encoder_stack(sd, "hintpath", hint_seq, pos_seq)                 # :186
     ref_logit = F.linear(dec, sd["trg_word_prj.weight"]).transpose(1, 2).reshape(N, N_VOCAB, h, w)  # :187-189
-    full = upfeat(dec.transpose(1, 2).reshape(N, 64, h, w), affinity, sp)  # :194-195
+    full = _q(upfeat(dec.transpose(1, 2).reshape(N, 64, h, w), affinity, sp))  # :194-195
     pred = torch.tanh(hourglass2(sd, torch.cat((gray, full), 1)))          # :196-197
     if stages is not None:
         stages.update(feats=feats, tokens=tokens, sizes=sizes, enc=enc, labels=labels, dec=dec, full=full)

@@ -62,3 +62,28 @@ def test_shard_bounds_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_native_choice_rows_is_numpys_stream():
+    """disco_host_choice_rows == `rows` x np.random.choice(S, K, replace=False) on numpy's global generator
+    (models/clusterkit.py:107): same index sets, same generator state afterwards, for full and sliced keeps, ragged
+    shapes, K == S and S == 1."""
+    from disentangledcolorization_b200 import _lib
+    for seed in (130, 1, 7, 2 ** 31 - 1):
+        for S, K, rows in ((256, 8, 64), (1024, 16, 5), (24, 5, 9), (8, 8, 3), (1, 1, 2), (300, 7, 4)):
+            np.random.seed(seed)
+            np.random.random(5)                                  # start somewhere inside the 624-word block
+            st = np.random.get_state()
+            want = np.stack([np.random.choice(S, K, replace=False) for _ in range(rows)])
+            nxt = np.random.randint(1 << 30)
+            np.random.set_state(st)
+            got = _lib.choice_rows(S, K, rows)
+            assert got.dtype == np.int32 and np.array_equal(got, want)
+            assert np.random.randint(1 << 30) == nxt
+            np.random.set_state(st)
+            lo, hi = 1, max(1, rows - 1)
+            part = _lib.choice_rows(S, K, rows, keep=(lo, hi))
+            assert np.array_equal(part, want[lo:hi]) and np.random.randint(1 << 30) == nxt
+    import pytest
+    with pytest.raises(_lib.DiscoError):
+        _lib.choice_rows(4, 5, 1)                                # more clusters than tokens (np.random.choice raises too)

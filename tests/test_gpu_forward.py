@@ -4,11 +4,14 @@ reference fixtures.
 Tolerances
   fp32 path : |d ab| <= 1e-3 on pred_colors (north-star gate), identical hint_mask, RNG streams advanced
               exactly as the reference advances them.
-  bf16 path : activations are stored in bf16 (8 mantissa bits) through ~50 stacked convolutions; with the
-              anchors injected (anchor choice is a discrete function of fp32-sensitive k-means) the stated
-              tolerance is max |d ab| <= 8e-2 and mean |d ab| <= 1e-2 against the fp32 oracle (measured: max 0.04-0.062,
-              mean 0.007 on the fixtures; the max moves by ~0.01 with the fp32 accumulation order of the conv kernels).
+  bf16 path : activations are stored in bf16 (8 mantissa bits) through ~50 stacked convolutions.  The tolerance is
+              DERIVED, not asserted: oracle/derive_bf16_tolerance.py runs the oracle in fp32 and again with bf16-rounded
+              conv weights / stored activations (torch CPU) on the fixture inputs, the benchmarked inputs and a 512x512
+              image; tests/golden/bf16_tolerance.json records max 0.057 / mean 0.0079 for that torch-vs-torch baseline and
+              the gate is 1.5 x that (0.0857 / 0.01178), anchors injected (anchor choice is a discrete function of
+              fp32-sensitive k-means).  The CUDA path measures max 0.04-0.062, mean 0.007: inside the baseline.
 """
+import json
 import os
 import sys
 
@@ -16,13 +19,15 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, golden_cases, load_golden, case_inputs
+from conftest import ROOT, GOLDEN, golden_cases, load_golden, case_inputs
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 pytestmark = pytest.mark.gpu
 
 FP32_AB_TOL = 1e-3
-BF16_AB_MAX, BF16_AB_MEAN = 8e-2, 1e-2
+with open(os.path.join(GOLDEN, "bf16_tolerance.json")) as _f:
+    _TOL = json.load(_f)
+BF16_AB_MAX, BF16_AB_MEAN = _TOL["BF16_AB_MAX"], _TOL["BF16_AB_MEAN"]
 
 
 def _model(sd, K, precision):
@@ -90,12 +95,17 @@ def test_forward_bf16_within_stated_tolerance(case, synth_sd):
     diff = np.abs(out[2].cpu().numpy() - g["pred_colors"])
     print(f"{case['name']}: bf16 max|d ab|={diff.max():.4f} mean={diff.mean():.5f}")
     assert diff.max() < BF16_AB_MAX and diff.mean() < BF16_AB_MEAN
-    # anchor agreement when bf16 runs its own k-means (reported, and required on these fixtures)
+    # anchor agreement when bf16 runs its own k-means: the bf16-emulating oracle keeps every anchor of these fixtures
+    # (bf16_tolerance.json rows: site_agreement 1.0), and so must the CUDA path; the batch-64 benchmark inputs, where
+    # bf16 k-means does move anchors, are gated in test_gpu_bench_config.py
     np.random.seed(case["seed"])
     torch.manual_seed(case["seed"])
     own = m(gray.cuda(), ab.cuda(), True, case["T"])
     agree = float((own[5].cpu().numpy() == g["hint_mask"]).mean())
     print(f"{case['name']}: bf16 anchor-site agreement {agree:.3f}")
+    assert agree == 1.0
+    d_own = np.abs(own[2].cpu().numpy() - g["pred_colors"])
+    assert d_own.max() < BF16_AB_MAX and d_own.mean() < BF16_AB_MEAN
 
 
 def test_forward_diverse_T2_matches_reference_fixture(synth_sd):
