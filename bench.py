@@ -249,6 +249,24 @@ def gpu_eager_baseline(sd, gray, ab, steps=3):
             wall = (time.perf_counter() - t0) / steps
             res[name] = {"ms_per_step": e0.elapsed_time(e1) / steps, "images_per_s": gray.shape[0] / wall,
                          "finite": bool(torch.isfinite(out[2].float()).all())}
+            # the three conv networks alone (cuDNN): the kernel-to-kernel comparison for the tcgen05 conv family, without
+            # the reference's python k-means loop and eager glue ops
+            feats65 = torch.cat((gray, torch.rand(gray.shape[0], 64, gray.shape[2], gray.shape[3], device=dev)), 1)
+
+            def convs():
+                with torch.no_grad():
+                    if ctx is None:
+                        O.spixelnet(sd_dev, gray); O.colorprobnet(sd_dev, gray); return O.hourglass2(sd_dev, feats65)
+                    with ctx:
+                        O.spixelnet(sd_dev, gray); O.colorprobnet(sd_dev, gray); return O.hourglass2(sd_dev, feats65)
+            convs()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                convs()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name]["conv_nets_only_ms"] = e0.elapsed_time(e1) / steps
         except Exception as e:   # e.g. an op without a bf16 autocast rule: report, do not fail the bench
             res[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
         torch.cuda.empty_cache()
@@ -462,7 +480,7 @@ def run_ours(args):
         chk = m(gray, ab, True, 0, init_idx=draws())
         g2 = ddist.gather_outputs(chk[2], world * B)
         parity["gather_slot_equal"] = bool(torch.equal(g2[rank * B:(rank + 1) * B], chk[2]))
-    log(f"parity check done: {parity}")
+    log(f"parity check done: { {k: v for k, v in parity.items() if not k.startswith('_')} }")
 
     line = None
     if rank == 0:
@@ -512,6 +530,8 @@ def run_ours(args):
             for k, v in eager.items():
                 if "images_per_s" in v:
                     v["speedup_ours_over_it"] = value / v["images_per_s"]
+                if "conv_nets_only_ms" in v:
+                    v["conv_speedup_ours_over_it"] = v["conv_nets_only_ms"] / conv_ms
             log(f"gpu eager baseline done: {eager}")
         # the CPU leg runs at N = 1 only (at N > 1 the other ranks would sit in the final barrier while rank 0 computes)
         skip_cpu = args.no_cpu_baseline or world > 1

@@ -18,7 +18,8 @@ EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create"
            "disco_reset_launch_count", "disco_add_launch_count", "disco_conv", "disco_poolfeat", "disco_upfeat", "disco_linear",
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
-           "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows"]
+           "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows",
+           "disco_encoder_stack", "disco_encoder_stack_pack", "disco_encoder_stack_scratch_elems"]
 
 
 class ConvSrc(C.Structure):
@@ -42,6 +43,11 @@ class LinearDesc(C.Structure):
                 ("col_scale", C.c_float), ("scale_cols", C.c_int32), ("relu", C.c_int32), ("residual", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("hint_mask", C.c_void_p), ("labels", C.c_void_p),
                 ("emb", C.c_void_p), ("transpose_S", C.c_int32), ("Y", C.c_void_p)]
+
+
+class EncoderLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b",
+                                          "n1_w", "n1_b", "n2_w", "n2_b")]
 
 
 _lib = None
@@ -77,6 +83,10 @@ def load():
     lib.disco_conv_tc_weight_elems.restype = C.c_int64
     lib.disco_conv_tc_pack_weights.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]
     lib.disco_conv_tc_cache_clear.argtypes = [C.c_void_p]
+    lib.disco_encoder_stack_scratch_elems.argtypes = [C.c_int, C.c_int]
+    lib.disco_encoder_stack_scratch_elems.restype = C.c_int64
+    lib.disco_encoder_stack_pack.argtypes = [C.POINTER(EncoderLayerWeights), C.c_int, C.c_void_p, C.c_void_p]
+    lib.disco_encoder_stack.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 3
     lib.disco_host_choice_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)] + [C.c_int] * 5 + [C.c_void_p]
     lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2

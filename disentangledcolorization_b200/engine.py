@@ -12,6 +12,7 @@ Responsibilities (plumbing only -- all arithmetic on the path runs in libdisco_b
 import collections
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -132,6 +133,28 @@ class Engine:
                                    n1_w=f(p + "norm1.weight"), n1_b=f(p + "norm1.bias"),
                                    n2_w=f(p + "norm2.weight"), n2_b=f(p + "norm2.bias")))
             self.stacks[stack] = layers
+        # fused tensor-core stack kernel (bf16 path): weights split into bf16 hi + lo 64x64 chunks by the library
+        self.fused_tokens = self.precision == "bf16" and os.environ.get("DISCO_TOKENS_FUSED", "1") != "0"
+        self.stack_packed = {}
+        if self.fused_tokens:
+            for stack in ("wildpath", "hintpath"):
+                arr = (_lib.EncoderLayerWeights * netspec.N_LAYERS)()
+                keep = []
+                for i in range(netspec.N_LAYERS):
+                    p = f"{stack}.layers.{i}."
+                    for field, key in (("in_w", "self_attn.in_proj_weight"), ("in_b", "self_attn.in_proj_bias"),
+                                       ("out_w", "self_attn.out_proj.weight"), ("out_b", "self_attn.out_proj.bias"),
+                                       ("l1_w", "linear1.weight"), ("l1_b", "linear1.bias"), ("l2_w", "linear2.weight"),
+                                       ("l2_b", "linear2.bias"), ("n1_w", "norm1.weight"), ("n1_b", "norm1.bias"),
+                                       ("n2_w", "norm2.weight"), ("n2_b", "norm2.bias")):
+                        t = sd[p + key].float().contiguous()
+                        keep.append(t)
+                        setattr(arr[i], field, t.data_ptr())
+                w = torch.empty(netspec.N_LAYERS * 12 * 2 * 4096, dtype=torch.int16)
+                vec = torch.empty(netspec.N_LAYERS * 832, dtype=torch.float32)
+                _lib.check(self.lib.disco_encoder_stack_pack(arr, netspec.N_LAYERS, C.c_void_p(w.data_ptr()),
+                                                             C.c_void_p(vec.data_ptr())), "disco_encoder_stack_pack")
+                self.stack_packed[stack] = (w.to(dev), vec.to(dev))
         self.mid_w = f("mid_word_prj.weight")
         self.trg_w = f("trg_word_prj.weight")
         emb = sd["trg_word_emb.weight"].float()
@@ -321,6 +344,14 @@ class Engine:
         """TransformerEncoder(use_dense_pos=True), 6 post-norm layers (models/transformer2d.py:17-28,52-60)."""
         tok, S = ws["tok"], ws["S"]
         pos = self._pos[(ws["h"], ws["w"])]
+        if self.fused_tokens and S <= 1024:      # one launch per stack (csrc/encoder_stack.cu); larger images: per-layer path
+            if "kv" not in tok:
+                n = int(self.lib.disco_encoder_stack_scratch_elems(B, S))
+                tok["kv"] = torch.zeros(n, dtype=torch.int16, device=self.device)
+            w, vec = self.stack_packed[stack]
+            _lib.check(self.lib.disco_encoder_stack(self.handle.h, _ptr(x_in), _ptr(pos), _ptr(w), _ptr(vec), netspec.N_LAYERS,
+                                                    B, S, _ptr(tok["kv"]), _ptr(out), stream), "disco_encoder_stack")
+            return
         x = x_in
         layers = self.stacks[stack]
         for i, L in enumerate(layers):

@@ -42,5 +42,36 @@ def main():
         print(f"encoder_tail M={M}:        {us:7.1f} us  ({M * (64 * 64 + 2 * 64 * 256) / us / 1e6:.1f} TFMA/s of ~36 peak)")
 
 
+def stacks():
+    """Whole 6-layer stack: fused one-launch kernel (bf16 engine) vs the per-layer fp32 SIMT path (fp32 engine)."""
+    from .. import synth
+    from ..engine import Engine
+    sd = synth.make_state_dict(seed=0)
+    dev = torch.device("cuda", 0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for B, H in ((64, 256), (32, 512)):
+        for prec in ("bf16", "fp32"):
+            eng = Engine(sd, dev, precision=prec, n_clusters=8)
+            # token buffers only (the conv workspace of the fp32 engine at batch 64 is not needed here)
+            S = (H // 16) ** 2
+            from ..engine import position_table
+            eng._pos[(H // 16, H // 16)] = position_table(H // 16, H // 16, dev)
+            M = B * S
+            f32 = dict(dtype=torch.float32, device=dev)
+            tok = dict(qkv=torch.empty(M, 192, **f32), att=torch.empty(M, 64, **f32), xa=torch.empty(M, 64, **f32),
+                       xb=torch.empty(M, 64, **f32))
+            ws = dict(tok=tok, S=S, h=H // 16, w=H // 16)
+            x = torch.randn(M, 64, **f32)
+            out = torch.empty(M, 64, **f32)
+            us = _time(lambda: eng._encoder_stack("wildpath", x, out, ws, B, st), iters=10)
+            flops = 6 * (2 * M * 64 * (192 + 64 + 512) + 4 * M * S * 64)
+            print(f"encoder stack ({'fused mma.sync split-bf16' if eng.fused_tokens else 'per-layer fp32 SIMT'}) B={B} S={S}: "
+                  f"{us:8.1f} us  = {flops / us / 1e6:.1f} TFLOP/s useful")
+
+
 if __name__ == "__main__":
+    import sys
+    if "--stacks" in sys.argv:
+        stacks()
+        sys.exit(0)
     main()

@@ -177,6 +177,31 @@ int disco_encoder_tail(disco_handle* h, const float* att, const float* x, float*
                        const float* bo, const float* ln1_g, const float* ln1_b, const float* w1, const float* b1,
                        const float* w2, const float* b2, const float* ln2_g, const float* ln2_b, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused encoder stack: `n_layers` EncoderLayers (models/transformer2d.py:52-60) = one TransformerEncoder.forward
+ * (models/transformer2d.py:17-28, use_dense_pos: pos added to q and k in every layer) in ONE launch.  Replaces the
+ * per-layer disco_linear / disco_attention / disco_encoder_tail sequence on the bf16 path (models/model.py:133,186).
+ * Tensor cores (mma.sync bf16, every operand split hi + lo -> fp32-grade products), tokens resident in registers,
+ * one CTA per 128 tokens, images of more than 128 tokens span a thread-block cluster (S <= 1024).
+ *   x_in, y   fp32 [B, S, 64] (may not alias);  pos fp32 [S, 64]
+ *   w_packed, vec: produced by disco_encoder_stack_pack from the layers' fp32 parameters (HOST pointers there):
+ *             w_packed bf16 [L][12][2][64][64], vec fp32 [L][832]
+ *   kv_scratch bf16, disco_encoder_stack_scratch_elems(B, S) elements (device; contents undefined between calls)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* in_w;  const float* in_b;    /* self_attn.in_proj_weight [192,64], in_proj_bias [192] */
+  const float* out_w; const float* out_b;   /* self_attn.out_proj.weight [64,64], bias [64] */
+  const float* l1_w;  const float* l1_b;    /* linear1 [256,64], [256] */
+  const float* l2_w;  const float* l2_b;    /* linear2 [64,256], [64] */
+  const float* n1_w;  const float* n1_b;    /* norm1 [64], [64] */
+  const float* n2_w;  const float* n2_b;    /* norm2 [64], [64] */
+} disco_encoder_layer_weights;
+int64_t disco_encoder_stack_scratch_elems(int batch, int S);
+int disco_encoder_stack_pack(const disco_encoder_layer_weights* layers, int n_layers, uint16_t* w_packed_host,
+                             float* vec_host);
+int disco_encoder_stack(disco_handle* h, const float* x_in, const float* pos, const uint16_t* w_packed, const float* vec,
+                        int n_layers, int batch, int S, uint16_t* kv_scratch, float* y, void* stream);
+
 /* Multi-head self-attention core: softmax(q k^T) v per (image, head); q already scaled.
  * Replaces the attention inside nn.MultiheadAttention (models/transformer2d.py:36,54).
  *   qkv [B*S, 192] (q | k | v, head h = columns 8h..8h+7 of each third) -> out [B*S, 64] */

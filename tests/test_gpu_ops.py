@@ -186,6 +186,36 @@ def test_encoder_stack_matches_oracle(synth_sd):
     assert (out.cpu().view(B, S, 64) - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 64, 96), (2, 256, 256), (1, 160, 160), (1, 512, 512), (5, 16, 16), (2, 176, 240)],
+                         ids=lambda v: str(v))
+def test_encoder_stack_fused_matches_oracle(synth_sd, B, H, W):
+    """The one-launch tensor-core stack (split-bf16 mma.sync, csrc/encoder_stack.cu) against the fp32 oracle stack:
+    S = 24 (one partly filled CTA), 256 (2-CTA cluster), 100 and 165 (ragged tails), 1024 (8-CTA cluster), 1 token."""
+    import disco_oracle as O
+    from disentangledcolorization_b200.engine import Engine
+    eng = Engine(synth_sd, _dev(), precision="bf16", n_clusters=1)
+    assert eng.fused_tokens
+    ws = eng._workspace(B, H, W)
+    S = ws["S"]
+    g = torch.Generator().manual_seed(7 + S)
+    x = torch.randn(B, S, 64, generator=g)
+    pos = O.position_sine(H // 16, W // 16).flatten(1).t().unsqueeze(0).expand(B, -1, -1)
+    for stack in ("wildpath", "hintpath"):
+        ref = O.encoder_stack(synth_sd, stack, x, pos)
+        out = torch.full((B * S, 64), float("nan"), device="cuda")
+        before = eng.handle.launches()
+        eng._encoder_stack(stack, x.cuda().view(B * S, 64).contiguous(), out, ws, B, _stream())
+        torch.cuda.synchronize()
+        assert eng.handle.launches() - before == 1
+        err = (out.cpu().view(B, S, 64) - ref).abs().max()
+        print(f"fused {stack} B={B} S={S}: max err {float(err):.2e}")
+        assert err < 1e-4, float(err)
+        # a second run into the ping-pong scratch gives the same bits (no stale key/value reads)
+        out2 = torch.empty_like(out)
+        eng._encoder_stack(stack, x.cuda().view(B * S, 64).contiguous(), out2, ws, B, _stream())
+        assert torch.equal(out, out2)
+
+
 def _kmeans_gpu(X, K, sizes, seed):
     from disentangledcolorization_b200 import _lib
     h = _handle()
