@@ -44,86 +44,110 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
-// grid (w, h, B), 256 threads.  feats NHWC C=64.
+// grid (w, h, B), 288 threads: warps 0..7 = (pixel column x, 4-channel group) over the cell's 16 rows, warp 8 = the four
+// scalar masses (ab0, ab1, soft mass, hard mass).  feats NHWC C=64.
+// r2: the affinity of the cell is staged pixel-major ([pixel][12]) so that a thread fetches all nine directions of a
+// pixel with three LDS.128 (one wavefront each) instead of nine scalar LDS -- the r1 kernel ran at the shared-memory
+// pipe's limit (1 LDS per 4 FMA) -- and the 36 scalar masses, which cost 180 warp shuffles per thread, now ride on a
+// ninth warp with the same row loop.
+constexpr int PKP = 12;           // floats per pixel in the staged affinity (9 used)
 template <typename T>
-__global__ void __launch_bounds__(256) poolfeat_partial_kernel(const T* __restrict__ feats, const float* __restrict__ ab,
+__global__ void __launch_bounds__(288) poolfeat_partial_kernel(const T* __restrict__ feats, const float* __restrict__ ab,
                                                                const float* __restrict__ aff, int H, int W,
                                                                float* __restrict__ partial) {
-  __shared__ float Pk[9][SP * SP];        // affinity of the cell's pixels
-  __shared__ float Red[16][9 * 64 + 1];   // cross-column reduction
-  __shared__ float Small[8][9 * 4];       // per-warp partials of (ab0, ab1, 1, hard) x 9
+  // phase 1-2: Pk[256][12]; phase 3 (after a barrier): Red[16][9*64] + RedX[32][36] over the same bytes
+  __shared__ __align__(16) float smem[16 * 9 * 64 + 32 * 36];
+  float* Pk = smem;
+  float* Red = smem;
+  float* RedX = smem + 16 * 9 * 64;
   const int cx = blockIdx.x, cy = blockIdx.y, n = blockIdx.z;
   const int tid = threadIdx.x;
   const size_t plane = (size_t)H * W;
   const int h = H / SP, w = W / SP;
 
-  // phase A: thread = pixel (row-major in the cell)
-  {
+  if (tid < 256) {                 // thread = pixel (row-major in the cell)
     const int py = tid >> 4, px = tid & 15;
     const size_t pix = (size_t)(cy * SP + py) * W + cx * SP + px;
-    float p[9], m = -1.f;
+    float p[PKP];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      p[k] = aff[((size_t)n * 9 + k) * plane + pix];
-      Pk[k][tid] = p[k];
-      m = fmaxf(m, p[k]);
-    }
-    const float a0 = ab ? ab[((size_t)n * 2 + 0) * plane + pix] : 0.f;
-    const float a1 = ab ? ab[((size_t)n * 2 + 1) * plane + pix] : 0.f;
-    float v[36];
+    for (int k = 0; k < 9; ++k) p[k] = aff[((size_t)n * 9 + k) * plane + pix];
+    p[9] = p[10] = p[11] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      v[k * 4 + 0] = p[k] * a0;
-      v[k * 4 + 1] = p[k] * a1;
-      v[k * 4 + 2] = p[k];
-      v[k * 4 + 3] = (p[k] == m) ? 1.f : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 36; ++i) {
-      float x = v[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if ((tid & 31) == 0) Small[tid >> 5][i] = x;
-    }
+    for (int q = 0; q < 3; ++q)
+      *reinterpret_cast<float4*>(Pk + tid * PKP + 4 * q) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
   }
   __syncthreads();
 
-  // phase B: thread = (column x, channel group of 4); loops over the 16 rows of the cell
-  {
-    const int x = tid >> 4, cg = tid & 15;
-    float acc[9][4];
+  float acc[9][4];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  for (int k = 0; k < 9; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  if (tid < 256) {
+    const int x = tid >> 4, cg = tid & 15;
     const T* base = feats + (((size_t)n * H + cy * SP) * W + cx * SP + x) * 64 + cg * 4;
 #pragma unroll 4
     for (int y = 0; y < SP; ++y) {
       float f[4];
       ld4<T>(base + (size_t)y * W * 64, f);
+      const float4 p0 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP);
+      const float4 p1 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP + 4);
+      const float p8 = Pk[(y * SP + x) * PKP + 8];
+      const float p[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(p[k], f[j], acc[k][j]);
+    }
+  } else {
+    // scalar masses: lane = (column x, half of the rows); acc[k] = (sum p_k ab0, sum p_k ab1, sum p_k, #pixels whose max is p_k)
+    const int lane = tid - 256, x = lane & 15, yh = lane >> 4;
+#pragma unroll 2
+    for (int yy = 0; yy < SP / 2; ++yy) {
+      const int y = yh * (SP / 2) + yy;
+      const size_t pix = (size_t)(cy * SP + y) * W + cx * SP + x;
+      const float a0 = ab ? ab[((size_t)n * 2 + 0) * plane + pix] : 0.f;
+      const float a1 = ab ? ab[((size_t)n * 2 + 1) * plane + pix] : 0.f;
+      const float4 p0 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP);
+      const float4 p1 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP + 4);
+      const float p8 = Pk[(y * SP + x) * PKP + 8];
+      const float p[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
+      float m = p[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k) m = fmaxf(m, p[k]);
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        const float p = Pk[k][y * SP + x];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(p, f[j], acc[k][j]);
+        acc[k][0] = fmaf(p[k], a0, acc[k][0]);
+        acc[k][1] = fmaf(p[k], a1, acc[k][1]);
+        acc[k][2] += p[k];
+        acc[k][3] += (p[k] == m) ? 1.f : 0.f;
       }
     }
+  }
+  __syncthreads();                 // every thread is done with Pk: the reduction buffers reuse its bytes
+  if (tid < 256) {
+    const int x = tid >> 4, cg = tid & 15;
 #pragma unroll
     for (int k = 0; k < 9; ++k)
+      *reinterpret_cast<float4*>(Red + x * (9 * 64) + k * 64 + cg * 4) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+  } else {
+    const int lane = tid - 256;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Red[x][k * 64 + cg * 4 + j] = acc[k][j];
+    for (int k = 0; k < 9; ++k)
+      *reinterpret_cast<float4*>(RedX + lane * 36 + k * 4) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
   }
   __syncthreads();
   float* out = partial + (((size_t)n * h + cy) * w + cx) * 9 * PART;
   const float inv = 1.0f / (SP * SP);   // avg_pool2d
-  for (int e = tid; e < 9 * 64; e += 256) {
+  for (int e = tid; e < 9 * 64; e += 288) {
     float s = 0.f;
 #pragma unroll
-    for (int x = 0; x < 16; ++x) s += Red[x][e];
+    for (int x = 0; x < 16; ++x) s += Red[x * (9 * 64) + e];
     out[(e >> 6) * PART + (e & 63)] = s * inv;
   }
   if (tid < 36) {
+    // same order of additions as a sum over the cell's pixels grouped by (half, column): deterministic
     float s = 0.f;
 #pragma unroll
-    for (int wg = 0; wg < 8; ++wg) s += Small[wg][tid];
+    for (int l = 0; l < 32; ++l) s += RedX[l * 36 + tid];
     out[(tid >> 2) * PART + 64 + (tid & 3)] = s * inv;
   }
 }
@@ -157,7 +181,7 @@ __global__ void poolfeat_gather_kernel(const float* __restrict__ partial, int h,
 template <typename T>
 __global__ void __launch_bounds__(256) upfeat_kernel(const float* __restrict__ tokens, const float* __restrict__ aff,
                                                      int H, int W, T* __restrict__ out) {
-  __shared__ float Pk[9][SP * SP];
+  __shared__ __align__(16) float Pk[SP * SP * PKP];   // pixel-major: three LDS.128 fetch a pixel's nine directions
   __shared__ float Tk[9][64];
   const int cx = blockIdx.x, cy = blockIdx.y, n = blockIdx.z;
   const int tid = threadIdx.x;
@@ -166,8 +190,13 @@ __global__ void __launch_bounds__(256) upfeat_kernel(const float* __restrict__ t
   {
     const int py = tid >> 4, px = tid & 15;
     const size_t pix = (size_t)(cy * SP + py) * W + cx * SP + px;
+    float p[PKP];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Pk[k][tid] = aff[((size_t)n * 9 + k) * plane + pix];
+    for (int k = 0; k < 9; ++k) p[k] = aff[((size_t)n * 9 + k) * plane + pix];
+    p[9] = p[10] = p[11] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      *reinterpret_cast<float4*>(Pk + tid * PKP + 4 * q) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
   }
   for (int e = tid; e < 9 * 64; e += 256) {
     const int k = e >> 6, c = e & 63;
@@ -185,11 +214,14 @@ __global__ void __launch_bounds__(256) upfeat_kernel(const float* __restrict__ t
 #pragma unroll 4
   for (int y = 0; y < SP; ++y) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4 p0 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP);
+    const float4 p1 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP + 4);
+    const float p8 = Pk[(y * SP + x) * PKP + 8];
+    const float pv[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float p = Pk[k][y * SP + x];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = fmaf(t[k][j], p, o[j]);
+      for (int j = 0; j < 4; ++j) o[j] = fmaf(t[k][j], pv[k], o[j]);
     }
     st4<T>(base + (size_t)y * W * 64, o);
   }
@@ -207,9 +239,9 @@ extern "C" int disco_poolfeat(disco_handle* h, int dtype, const void* feats, con
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(W / SP, H / SP, batch);
   if (dtype == DISCO_F32)
-    poolfeat_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)feats, ab, affinity, H, W, partial);
+    poolfeat_partial_kernel<float><<<grid, 288, 0, st>>>((const float*)feats, ab, affinity, H, W, partial);
   else
-    poolfeat_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)feats, ab, affinity, H, W, partial);
+    poolfeat_partial_kernel<__nv_bfloat16><<<grid, 288, 0, st>>>((const __nv_bfloat16*)feats, ab, affinity, H, W, partial);
   DISCO_LAUNCH_CHECK(h);
   poolfeat_gather_kernel<<<batch * (H / SP) * (W / SP), 64, 0, st>>>(partial, H / SP, W / SP, tokens, spix_ab, conf, sizes);
   DISCO_LAUNCH_CHECK(h);

@@ -29,9 +29,11 @@ BF16_AB_MAX, BF16_AB_MEAN = TOL["BF16_AB_MAX"], TOL["BF16_AB_MEAN"]
 # while 98.8 % of the 256 sites agree (~1.5 of 8 anchors move per image).  The floors below are that baseline / the B200
 # measurement (printed by the test) minus a margin; moved anchors change colours by an anchor flip, which
 # is why the |d ab| gate with identical anchors is the parity statement and this is the agreement statement.
-MIN_IMAGES_SAME_ANCHORS = 0.10
-MIN_SITE_AGREEMENT = 0.975
-MIN_ANCHOR_OVERLAP = 0.70
+# Measured on B200 (round 2, 64 benchmark images): 26/64 images with all 8 anchors identical, site agreement 0.9927,
+# anchor overlap 0.883 (on average 7.1 of 8 anchors are the reference's).
+MIN_IMAGES_SAME_ANCHORS = 0.25
+MIN_SITE_AGREEMENT = 0.985
+MIN_ANCHOR_OVERLAP = 0.80
 
 
 def _model(sd, K, precision):
