@@ -218,6 +218,9 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ void lds2x64(uint32_t saddr, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(saddr));
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -512,14 +515,24 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
             }
             if constexpr (BN <= 64) {
               if (P.gray) {
+                // fp32 L-channel taps as packed fp32 pairs (FFMA2): 9 x CH/2 instead of 9 x CH FMAs per pixel, the
+                // weight pairs come straight out of LDS.128 as two 64-bit operands
+                f32x2 v2[CH / 2];
 #pragma unroll
-                for (int t = 0; t < 9; ++t)
+                for (int j = 0; j < CH / 2; ++j) v2[j] = pack2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  const f32x2 G = pack2(g[t], g[t]);
 #pragma unroll
                   for (int j = 0; j < CH; j += 4) {
-                    const float4 wv = lds128(wp + 4 * ((3 + t) * COLS + c0 - col0 + j));
-                    v[j] = fmaf(g[t], wv.x, v[j]); v[j + 1] = fmaf(g[t], wv.y, v[j + 1]);
-                    v[j + 2] = fmaf(g[t], wv.z, v[j + 2]); v[j + 3] = fmaf(g[t], wv.w, v[j + 3]);
+                    f32x2 w01, w23;
+                    lds2x64(wp + 4 * ((3 + t) * COLS + c0 - col0 + j), w01, w23);
+                    v2[j / 2] = ffma2(G, w01, v2[j / 2]);
+                    v2[j / 2 + 1] = ffma2(G, w23, v2[j / 2 + 1]);
                   }
+                }
+#pragma unroll
+                for (int j = 0; j < CH / 2; ++j) unpack2(v2[j], v[2 * j], v[2 * j + 1]);
               }
             }
             }

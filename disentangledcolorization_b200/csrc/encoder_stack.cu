@@ -66,12 +66,6 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// D(16x8, fp32) += A(16x8, bf16, row) * B(8x8, bf16, col)
-__device__ __forceinline__ void mma1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(b0));
-}
 __device__ __forceinline__ float es_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -309,13 +303,16 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
         uint32_t kh[4], kl[4];
         ldsm_x4(kh, la + h * 16);
         ldsm_x4(kl, la + 32 * ES_ROWB + h * 16);
+        // head dimension 8 = half a k16 step: A = [q_hi | q_lo] against B = [k_hi ; k_hi] gives q_hi k_hi + q_lo k_hi in one
+        // instruction, against [k_lo ; k_lo] the remaining cross term (+ the negligible lo*lo).  Measured on B200: an
+        // m16n8k8 issues at the same 2 clk/SM as an m16n8k16, so three k8 products would cost 6 clk, these two cost 4.
+        const uint32_t qa[4] = {qh[h][0], qh[h][1], ql[h][0], ql[h][1]};
         float s[4][4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-          mma1688(s[n], qh[h][0], qh[h][1], kh[n]);
-          mma1688(s[n], ql[h][0], ql[h][1], kh[n]);
-          mma1688(s[n], qh[h][0], qh[h][1], kl[n]);
+          mma16816(s[n], qa, kh[n], kh[n]);
+          mma16816(s[n], qa, kl[n], kl[n]);
         }
         if (tail) {
 #pragma unroll
