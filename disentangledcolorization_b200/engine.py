@@ -74,6 +74,14 @@ class _PackedConv:
         self.post_shift = folded.post_shift.to(device) if folded.post_shift is not None else None
 
 
+class _FusedOp:
+    """Profile record of a launch that covers several ConvOps of the plan (same fields profile_convs reads)."""
+
+    def __init__(self, name, ops):
+        self.name, self.ops = name, ops
+        self.cout, self.cin, self.stride, self.kind, self.srcs = ops[-1].cout, ops[0].cin, 1, "fused", ops[0].srcs
+
+
 class Engine:
     def __init__(self, state_dict, device, precision="bf16", n_clusters=8, sp_size=16, enhanced=True, random_hint=False):
         if precision not in _DT:
@@ -120,6 +128,16 @@ class Engine:
                 for f in self._maybe_split(netspec.fold(sd, op)):
                     packed.append(_PackedConv(f, dev))
             self.convs[name] = packed
+        # fused head of SpixelNet (conv0a -> conv0b -> conv1a in one launch, csrc/segnet_fused.cu), bf16 path
+        self.seg_head = None
+        seg = self.convs["segnet"]
+        if (self.precision == "bf16" and os.environ.get("DISCO_SEG_FUSED", "1") != "0"
+                and [pc.op.name.rsplit(".", 1)[-1] for pc in seg[:3]] == ["conv0a", "conv0b", "conv1a"]):
+            def tc_pack(pc, cin, cout):          # fp32 [tap][cin][cout] -> bf16 [tap][cout][cin]
+                w = pc.w32_host.view(9, cin, cout).permute(0, 2, 1).contiguous().to(torch.bfloat16)
+                return w.view(torch.int16).to(dev)
+            self.seg_head = dict(w0b=tc_pack(seg[1], 16, 16), w1a=tc_pack(seg[2], 16, 32), slope=float(seg[0].op.slope),
+                                 op=_FusedOp("segnet.net.conv0a+conv0b+conv1a", [pc.op for pc in seg[:3]]))
         f = lambda k: sd[k].float().contiguous().to(dev)
         self.stacks = {}
         for stack in ("wildpath", "hintpath"):
@@ -316,7 +334,21 @@ class Engine:
             ws["descs"] = {k: v for k, v in ws["descs"].items() if k[0] != net}
             ws["descs"][key] = descs
         prof = self._prof
-        for d, (pc, _, _) in zip(descs, ws["plans"][net]):
+        skip = 0
+        if net == "segnet" and self.seg_head is not None:
+            sh, seg = self.seg_head, self.convs["segnet"]
+            H, W = gray.shape[2], gray.shape[3]
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _lib.check(self.lib.disco_segnet_head(self.handle.h, _ptr(gray), _ptr(seg[0].w32), _ptr(seg[0].bias), _ptr(sh["w0b"]),
+                                                  _ptr(seg[1].bias), _ptr(sh["w1a"]), _ptr(seg[2].bias), sh["slope"], B, H, W,
+                                                  _ptr(bufs["sg.out1"]), _ptr(bufs["sg.1a"]), stream), "disco_segnet_head")
+            if prof is not None:
+                e1.record()
+                prof.append((sh["op"], B, H, W, e0, e1))
+            skip = 3
+        for d, (pc, _, _) in list(zip(descs, ws["plans"][net]))[skip:]:
             if prof is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -570,6 +602,8 @@ class Engine:
     def algorithmic_flops(op, B, Ho, Wo):
         """2 x MACs of the reference's own formulation of this op (9 taps at the output resolution for
         nn.Upsample -> conv; 16 taps per input pixel for ConvTranspose2d)."""
+        if op.kind == "fused":
+            return sum(Engine.algorithmic_flops(o, B, Ho // o.scale, Wo // o.scale) for o in op.ops)
         if op.kind == "deconv4":
             return 2.0 * B * (Ho // 2) * (Wo // 2) * op.cin * op.cout * 16
         return 2.0 * B * Ho * Wo * op.cin * op.cout * 9
@@ -578,6 +612,8 @@ class Engine:
     def executed_flops(op, B, Ho, Wo):
         """2 x MACs the kernels actually issue: a nearest-upsampled source is convolved as four 2x2-tap parity phases
         on the low-resolution map (4/9 of the reference formulation's MACs); everything else equals algorithmic_flops."""
+        if op.kind == "fused":
+            return sum(Engine.executed_flops(o, B, Ho // o.scale, Wo // o.scale) for o in op.ops)
         if op.kind == "deconv4":
             return 2.0 * B * (Ho // 2) * (Wo // 2) * op.cin * op.cout * 16
         f = 0.0

@@ -126,6 +126,18 @@ int disco_conv_tc_cache_clear(disco_handle* h);
 int disco_debug_timeline(long long* out_host);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused head of SpixelNet: conv0a -> conv0b -> conv1a (models/network.py:264-266,293-295; conv(no bias) + BatchNorm +
+ * LeakyReLU each, BatchNorm folded) in one launch on the bf16 path.  The 16-channel intermediate of conv0a stays in
+ * shared memory; only the tensors later layers read are written: out1 = conv0b output (NHWC bf16 [B,H,W,16]) and
+ * a1 = conv1a output (NHWC bf16 [B,H/2,W/2,32]).
+ *   gray fp32 [B,H,W];  w0a fp32 [9][16], w0b bf16 [9][16 co][16 ci], w1a bf16 [9][32 co][16 ci] (taps row-major,
+ *   BatchNorm scale folded in), b0a/b0b/b1a fp32 folded biases;  slope = LeakyReLU negative slope (0.1)
+ * ------------------------------------------------------------------------------------------- */
+int disco_segnet_head(disco_handle* h, const float* gray, const float* w0a, const float* b0a, const uint16_t* w0b,
+                      const float* b0b, const uint16_t* w1a, const float* b1a, float slope, int batch, int H, int W,
+                      void* out1, void* a1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Super-pixel pooling.  Replaces basic.poolfeat (models/basic.py:274-324) applied to
  * cat[pred_feats, input_colors] and basic.get_spixel_size (models/basic.py:327-335), i.e.
  * models/model.py:114-117,121, in one pass over the feature map.

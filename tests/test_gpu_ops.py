@@ -216,6 +216,47 @@ def test_encoder_stack_fused_matches_oracle(synth_sd, B, H, W):
         assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 48, 80), (3, 16, 16), (1, 256, 256), (2, 144, 112)], ids=lambda v: str(v))
+def test_segnet_fused_head_matches_layer_by_layer(synth_sd, B, H, W):
+    """conv0a -> conv0b -> conv1a in one launch (csrc/segnet_fused.cu, 16-channel intermediate in shared memory) against
+    the same three layers launched one by one (tcgen05 / CUDA-core kernels) and against torch fp32: partial tiles, tiles
+    on every image border, images smaller than a tile."""
+    import torch.nn.functional as F
+    from disentangledcolorization_b200 import synth, netspec
+    from disentangledcolorization_b200.engine import Engine
+    gray = torch.from_numpy(synth.make_gray(B, H, W, seed=17 + H)).cuda()
+    outs = {}
+    for fused in (True, False):
+        eng = Engine(synth_sd, _dev(), precision="bf16", n_clusters=1)
+        assert eng.seg_head is not None
+        if not fused:
+            eng.seg_head = None
+        ws = eng._workspace(B, H, W)
+        before = eng.handle.launches()
+        eng._run_net("segnet", ws, B, gray, _stream())
+        torch.cuda.synchronize()
+        outs[fused] = (ws["bufs"]["sg.out1"].float().cpu(), ws["bufs"]["sg.1a"].float().cpu(), ws["bufs"]["affinity"].cpu(),
+                       eng.handle.launches() - before)
+    assert outs[False][3] - outs[True][3] == 2                       # three launches became one
+    # torch fp32 on the folded weights
+    ops = netspec.segnet_ops()[:3]
+    x = gray.cpu()
+    ref = []
+    for op in ops:
+        f = netspec.fold(synth_sd, op)
+        x = F.leaky_relu(F.conv2d(x, f.weights[0], f.bias, stride=op.stride, padding=1), 0.1)
+        ref.append(x.permute(0, 2, 3, 1))
+    for i, name in ((0, "out1"), (1, "conv1a")):
+        a, b, r = outs[True][i], outs[False][i], ref[i + 1]
+        scale = float(r.abs().max())
+        print(f"{name}: fused vs layer-by-layer max {float((a - b).abs().max()):.3e}, fused vs torch fp32 max "
+              f"{float((a - r).abs().max()):.3e} (layer-by-layer: {float((b - r).abs().max()):.3e}), scale {scale:.2f}")
+        assert float((a - r).abs().max()) < 2e-2 * scale            # two / three bf16-stored layers
+        assert float((a - b).abs().max()) < 1e-2 * scale            # same arithmetic, different fp32 summation order
+        assert float((a - b).abs().mean()) < 5e-4 * scale
+    assert float((outs[True][2] - outs[False][2]).abs().max()) < 2e-2
+
+
 def _kmeans_gpu(X, K, sizes, seed):
     from disentangledcolorization_b200 import _lib
     h = _handle()
