@@ -47,9 +47,9 @@ struct SgParams {
 };
 
 struct SgSmem {
-  float gray[RGH * RGW];
-  float w0a[9 * 16 + 16];
-  float bias[16 + 32];
+  __align__(16) float gray[(RGH * RGW + 3) / 4 * 4];
+  __align__(16) float w0a[9 * 16 + 16];      // read as float4
+  __align__(16) float bias[16 + 32];         // read as float2
   __align__(16) uint16_t w0b[9 * 16 * 16];
   __align__(16) uint16_t w1a[9 * 32 * 16];
   __align__(16) uint8_t t0a[N0 * P16];        // conv0a output (+1 halo), later reused to stage conv1a's output tile
