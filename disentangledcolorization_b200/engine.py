@@ -111,6 +111,7 @@ class Engine:
         self.use_graph = False        # replay the whole forward from a CUDA graph (fixed shapes, sampled_T == 0)
         self.static_outputs = False   # graph mode: return the graph-owned output tensors (valid until the next forward)
         self.lazy_rng = False         # advance torch's CPU generator at the next forward / sync_rng() instead of syncing now
+        self.batched_diverse = False  # extension: sampled_T > 0 on batches (3N variants, variant-major)
         self._graphs = {}
         self.load_state_dict(state_dict)
 
@@ -499,9 +500,10 @@ class Engine:
         B, _, H, W = gray.shape
         if B == 0:
             raise _lib.DiscoError("empty batch")
-        if sampled_T > 0 and B != 1:
+        if sampled_T > 0 and B != 1 and not self.batched_diverse:
             raise _lib.DiscoError("sampled_T > 0 (--diverse) needs a batch of 1, as in the reference "
-                                  "(the expand at models/model.py:155-159 fails otherwise)")
+                                  "(the expand at models/model.py:155-159 fails otherwise); set model.batched_diverse = True "
+                                  "for the batched extension")
         dev = self.device
         gray = gray.to(device=dev, dtype=torch.float32).contiguous()
         ab = ab.to(device=dev, dtype=torch.float32).contiguous()
@@ -556,17 +558,17 @@ class Engine:
                 self._pending_rng = (state, tok["events_host"], ev, S)
 
         # ---- anchor colours and token labels (model.py:142-168)
-        if sampled_T > 0:                                                               # model.py:148-159, N = 3
-            B2 = 3
+        if sampled_T > 0:                                                               # model.py:148-159, N = 3 (x B: extension)
+            B2 = 3 * B
             ws2 = self._workspace(B2, H, W)
             tok2 = ws2["tok"]
-            spix_colors = torch.empty(3, 2, h, w, dtype=torch.float32, device=dev)
-            _lib.check(lib.disco_token_sample3(hd, _ptr(pal_logit), _ptr(self.q_to_ab), 1, S, _ptr(tok2["labels"]),
+            spix_colors = torch.empty(B2, 2, h, w, dtype=torch.float32, device=dev)
+            _lib.check(lib.disco_token_sample3(hd, _ptr(pal_logit), _ptr(self.q_to_ab), B, S, _ptr(tok2["labels"]),
                                                _ptr(spix_colors), stream), "disco_token_sample3")
-            tok2["tokens"].copy_(tok["tokens"].expand(3, -1, -1))
-            hint = hint.expand(3, -1, -1, -1).contiguous()
-            gray2 = gray.expand(3, -1, -1, -1).contiguous()
-            ws2["bufs"]["affinity"].copy_(affinity.expand(3, -1, -1, -1))
+            tok2["tokens"].copy_(tok["tokens"].repeat(3, 1, 1))                         # variant-major: index v * B + n
+            hint = hint.repeat(3, 1, 1, 1)
+            gray2 = gray.repeat(3, 1, 1, 1)
+            ws2["bufs"]["affinity"].copy_(affinity.repeat(3, 1, 1, 1))
         else:
             B2, ws2, tok2, gray2 = B, ws, tok, gray
             spix_colors = torch.empty(B, 2, h, w, dtype=torch.float32, device=dev)

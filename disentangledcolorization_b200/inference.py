@@ -10,6 +10,7 @@ like util.save_normLabs_from_batch, utils/util.py:91-106).  Extensions: --batch 
 into one forward (the reference processes one image per call), --precision {bf16,fp32}.
 """
 import argparse
+import collections
 import datetime
 import glob
 import os
@@ -60,8 +61,28 @@ def load_checkpoint(checkpt_path, model):
     return model
 
 
+def _fetch_np(img_path, no_resize):
+    """fetch_data for the reader threads: numpy (1,H,W) gray, (2,H,W) ab and the original size (cv2 releases the GIL)."""
+    gray, ab, hw = fetch_data(img_path, no_resize)
+    return gray[0].numpy(), ab[0].numpy(), hw
+
+
+def _save_rgb(path, rgb):
+    """PNG writer for the writer threads (cv2 releases the GIL while encoding; pixels equal PIL's Image.save)."""
+    import cv2
+    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)):
+        raise IOError(f"cannot write {path}")
+
+
 def test_model(args):
-    from . import basic, model as disco_model
+    """reference main/colorizer/inference.py:56-139, restructured as a pipeline: reader threads decode /
+    resize / convert to Lab, images of equal size are grouped (in sorted order, so the host RNG is consumed per image
+    exactly as one image per forward would consume it) into batches of --batch, `ColorizePipeline` overlaps H2D, forward and
+    D2H of neighbouring batches, Lab -> RGB uint8 runs on the device (disco_lab2rgb_u8), writer threads encode the PNGs."""
+    import concurrent.futures as cf
+    import ctypes as C
+    from . import _lib, model as disco_model
+    from .pipeline import ColorizePipeline
     print("@Inference: [%s] (spixel-size=%d)" % (args.model, args.psize))
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
@@ -80,44 +101,84 @@ def test_model(args):
     load_checkpoint(args.checkpt, net)
     print("-weight loaded successfully.")
     net = net.cuda().eval()
+    net.batched_diverse = True
+    dev = torch.device("cuda", torch.cuda.current_device())
+    handle = _lib.Handle.get(dev.index)
+    sampled_T = 2 if args.diverse else 0
+    n_var = 3 if args.diverse else 1
     start = time.time()
-    n_done = 0
-    pending = []
+    n_threads = max(1, args.io_threads)
+    readers = cf.ThreadPoolExecutor(n_threads)
+    writers = cf.ThreadPoolExecutor(n_threads)
+    window = max(2 * args.batch, 2 * n_threads)          # decoded images in flight
+    metas, writes = [], []                                # per batch: [(file name, (H, W)), ...]; pending PNG writes
 
-    def flush():
-        nonlocal n_done
-        if not pending:
-            return
-        grays = torch.cat([p[0] for p in pending]).cuda(non_blocking=True)
-        abs_ = torch.cat([p[1] for p in pending]).cuda(non_blocking=True)
-        sampled_T = 2 if args.diverse else 0
-        out = net(grays, abs_, True, sampled_T)
-        enhanced = out[2]
-        if args.diverse:
-            for no in range(3):
-                lab = basic.tensor2array(torch.cat((grays, enhanced[no:no + 1]), dim=1))
-                H, W = pending[0][3]
-                lab = lab[:, :H, :W, :] if args.no_resize else lab
-                save_lab_batch(lab, save_dir, [pending[0][2]], suffix="c%d" % no)
-        else:
-            lab = basic.tensor2array(torch.cat((grays, enhanced), dim=1))
-            for i, (_, _, name, (H, W)) in enumerate(pending):
-                one = lab[i:i + 1, :H, :W, :] if args.no_resize else lab[i:i + 1]
-                save_lab_batch(one, save_dir, [name])
-        n_done += len(pending)
-        pending.clear()
+    def batches():
+        """Consecutive images of equal (padded) size, at most --batch per forward, staged in pinned memory."""
+        pending = collections.deque()
+        it = iter(img_list)
 
-    for img_path in img_list:
-        fname = os.path.splitext(os.path.basename(img_path))[0] + ".png"
-        print("-processing %s ..." % os.path.basename(img_path))
-        gray, ab, hw = fetch_data(img_path, args.no_resize)
-        if pending and (len(pending) >= args.batch or pending[0][0].shape != gray.shape or args.diverse):
-            flush()
-        pending.append((gray, ab, fname, hw))
-        if len(pending) >= args.batch or args.diverse:
-            flush()
-    flush()
-    print("-processed %d imgs. consumed %f sec" % (n_done, time.time() - start))
+        def refill():
+            while len(pending) < window:
+                path = next(it, None)
+                if path is None:
+                    return
+                print("-processing %s ..." % os.path.basename(path))
+                pending.append((path, readers.submit(_fetch_np, path, args.no_resize)))
+
+        refill()
+        group = []
+        while pending or group:
+            item = None
+            if pending:
+                path, fut = pending.popleft()
+                refill()
+                g, a, hw = fut.result()
+                item = (os.path.splitext(os.path.basename(path))[0] + ".png", g, a, hw)
+            if group and (item is None or len(group) >= args.batch or group[0][1].shape != item[1].shape):
+                gray = torch.empty(len(group), 1, *group[0][1].shape[1:]).pin_memory()
+                ab = torch.empty(len(group), 2, *group[0][1].shape[1:]).pin_memory()
+                for i, (_, g_, a_, _) in enumerate(group):
+                    gray[i] = torch.from_numpy(g_)
+                    ab[i] = torch.from_numpy(a_)
+                metas.append([(nm, hw_) for nm, _, _, hw_ in group])
+                yield gray, ab
+                group = []
+            if item is not None:
+                group.append(item)
+
+    def to_rgb(out, gray, ab):
+        """compute stream, right after the forward: Lab -> RGB uint8 for every variant of every image of the batch"""
+        pred = out[2]
+        B, _, H, W = gray.shape
+        g = gray if n_var == 1 else gray.repeat(n_var, 1, 1, 1)
+        rgb = torch.empty(pred.shape[0], H, W, 3, dtype=torch.uint8, device=pred.device)
+        _lib.check(handle.lib.disco_lab2rgb_u8(handle.h, C.c_void_p(g.data_ptr()), C.c_void_p(pred.data_ptr()), pred.shape[0], H, W,
+                                               H, W, C.c_void_p(rgb.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "disco_lab2rgb_u8")
+        return rgb
+
+    def on_result(i, host):
+        """host thread, batch i has landed in pinned memory: crop the padding off, hand the images to the writer threads"""
+        arr = host.numpy()
+        B = len(metas[i])
+        for v in range(n_var):
+            for k, (name, (H, W)) in enumerate(metas[i]):
+                img = arr[v * B + k]
+                img = img[:H, :W] if args.no_resize else img
+                out_name = name.replace(".png", "-c%d.png" % v) if args.diverse else name
+                writes.append(writers.submit(_save_rgb, os.path.join(save_dir, out_name), np.ascontiguousarray(img)))
+
+    pipe = ColorizePipeline(net, device=dev, sampled_T=sampled_T)
+    pipe.run(batches(), post=to_rgb, on_result=on_result, keep="none")
+    for w in writes:
+        w.result()
+    readers.shutdown()
+    writers.shutdown()
+    n_done = sum(len(m) for m in metas)
+    dt = time.time() - start
+    print("-processed %d imgs. consumed %f sec" % (n_done, dt))
+    return n_done, dt
 
 
 def build_parser():
@@ -142,6 +203,8 @@ def build_parser():
     # extensions
     p.add_argument("--batch", default=1, type=int, help="[extension] images per forward (equal sizes only)")
     p.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="[extension] bf16 tensor-core or fp32 exact path")
+    p.add_argument("--io_threads", default=min(16, os.cpu_count() or 4), type=int,
+                   help="[extension] reader (decode/resize/Lab) and writer (PNG) threads around the GPU pipeline")
     return p
 
 
@@ -150,7 +213,7 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     args.dense_pos = True                 # reference inference.py:165-166
     args.model = "AnchorColorProb"
-    test_model(args)
+    return test_model(args)
 
 
 if __name__ == "__main__":

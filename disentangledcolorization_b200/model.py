@@ -42,6 +42,9 @@ class AnchorColorProb(nn.Module):
     use_cuda_graph = False
     #: graph mode only: return the graph-owned output tensors (overwritten by the next forward) instead of copies
     graph_static_outputs = False
+    #: [extension, SURVEY 8f N2] allow sampled_T > 0 (--diverse) on batches: the reference's expand (models/model.py:155-159)
+    #: only works for N == 1; with this flag a batch of N returns 3N variants, variant-major (index v * N + n)
+    batched_diverse = False
     #: defer the host-RNG fix-up (one tiny D2H read + sync) to the next forward / engine().sync_rng()
     lazy_rng = False
 
@@ -127,6 +130,7 @@ class AnchorColorProb(nn.Module):
         self._engine.use_graph = self.use_cuda_graph
         self._engine.static_outputs = self.graph_static_outputs
         self._engine.lazy_rng = self.lazy_rng
+        self._engine.batched_diverse = self.batched_diverse
         return self._engine
 
     def forward(self, input_grays, input_colors, test_mode=False, sampled_T=0, hint_mask=None, init_idx=None):

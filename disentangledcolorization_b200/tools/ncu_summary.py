@@ -84,9 +84,44 @@ def full(pairs, prefix):
     return "\n".join(lines)
 
 
+def kernels(rep, hbm_peak_gbs=None):
+    """One markdown row per captured launch of a `--set full` report: duration, DRAM bytes, achieved GB/s (and fraction of
+    the measured HBM peak), tensor / SM / L1 / issue utilisation -- the table for the HBM-bound kernels."""
+    import os
+    if hbm_peak_gbs is None:
+        peaks = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "MEASURED_PEAKS.json")
+        hbm_peak_gbs = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, k, default="nan"):
+        return r[col[k]] if k in col and r[col[k]] != "" else default
+    out = ["| kernel | grid x block | ncu duration | DRAM read + write | achieved | of measured HBM peak | tensor pipe | SM throughput | "
+           "L1/shared throughput | issue slots | regs |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+    for r in rows[2:]:
+        dur_us = float(val(r, "gpu__time_duration.sum").replace(",", ""))
+        if units[col["gpu__time_duration.sum"]] == "ms":
+            dur_us *= 1e3
+        elif units[col["gpu__time_duration.sum"]] == "ns":
+            dur_us /= 1e3
+        dram = _to_bytes(val(r, "dram__bytes_read.sum"), units[col["dram__bytes_read.sum"]]) + \
+            _to_bytes(val(r, "dram__bytes_write.sum"), units[col["dram__bytes_write.sum"]])
+        gbs = dram / dur_us / 1e3
+        f = lambda k: f"{float(val(r, k)):.1f} %" if val(r, k) != "nan" else "-"
+        out.append(f"| `{_short(val(r, 'Kernel Name'))}` | {val(r, 'Grid Size')} x {val(r, 'Block Size')} | {dur_us:.1f} us | {dram / 1e6:.1f} MB | "
+                   f"{gbs:.0f} GB/s | {100 * gbs / hbm_peak_gbs:.1f} % | {f('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')} | "
+                   f"{f('sm__throughput.avg.pct_of_peak_sustained_elapsed')} | {f('l1tex__throughput.avg.pct_of_peak_sustained_elapsed')} | "
+                   f"{f('smsp__issue_active.avg.pct_of_peak_sustained_active')} | {val(r, 'launch__registers_per_thread')} |")
+    print("\n".join(out))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "kernels":
+        kernels(sys.argv[2])
     else:
         prefix = sys.argv[sys.argv.index("--out-prefix") + 1]
         pairs = [a.split("=", 1) for a in sys.argv[2:] if "=" in a and not a.startswith("--")]

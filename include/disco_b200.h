@@ -251,6 +251,13 @@ int disco_token_labels(disco_handle* h, int mode, const float* src, const float*
 int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
                         int32_t* labels3, float* colors3, void* stream);
 
+/* Lab -> sRGB uint8, the image the CLI saves (main/colorizer/inference.py:119-127 + utils/util.py:91-106:
+ * L = (gray + 1) * 50, ab * 110, cv2.cvtColor(COLOR_LAB2RGB) on float32, * 255, astype(uint8)).
+ *   gray fp32 [B,1,H,W], ab fp32 [B,2,H,W] (normalised, as the forward returns pred_colors);
+ *   rgb uint8 [B, crop_h, crop_w, 3] = the top-left crop_h x crop_w pixels (--no_resize de-padding) */
+int disco_lab2rgb_u8(disco_handle* h, const float* gray, const float* ab, int batch, int H, int W, int crop_h, int crop_w,
+                     uint8_t* rgb, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host helper (no device work): the k-means initialisation draws of clusterkit.initialize
  * (models/clusterkit.py:99-109), `np.random.choice(S, K, replace=False)` once per image in batch order, for `rows`

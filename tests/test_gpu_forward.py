@@ -126,6 +126,29 @@ def test_forward_diverse_T2_matches_reference_fixture(synth_sd):
         m(torch.zeros(2, 1, 64, 64).cuda(), torch.zeros(2, 2, 64, 64).cuda(), True, 2)   # N must be 1, as in the reference
 
 
+def test_diverse_batched_extension_equals_single_image_runs(synth_sd):
+    """--diverse beyond N = 1.  With model.batched_diverse a batch of N returns 3N variants (variant-major),
+    each equal to what the N == 1 path (the only one the reference supports) returns for that image."""
+    from disentangledcolorization_b200 import synth
+    m = _model(synth_sd, 4, "fp32")
+    gray = torch.from_numpy(synth.make_gray(3, 64, 64, seed=61)).cuda()
+    ab = torch.zeros(3, 2, 64, 64).cuda()
+    with pytest.raises(Exception):
+        m(gray, ab, True, 2)                                     # reference behaviour without the flag
+    np.random.seed(8)
+    torch.manual_seed(8)
+    singles = [m(gray[i:i + 1], ab[i:i + 1], True, 2) for i in range(3)]
+    m.batched_diverse = True
+    np.random.seed(8)
+    torch.manual_seed(8)
+    out = m(gray, ab, True, 2)
+    assert tuple(out[2].shape) == (9, 2, 64, 64) and tuple(out[1].shape) == (9, 313, 4, 4) and tuple(out[5].shape) == (9, 1, 4, 4)
+    for n in range(3):
+        for v in range(3):
+            for j in (1, 2, 4, 5):
+                assert torch.equal(out[j][v * 3 + n], singles[n][j][v]), (n, v, j)
+
+
 def test_random_hint_mode_matches_oracle(synth_sd):
     """--random_hint: anchors from python's random.sample (basic.py:42-47) instead of k-means."""
     import random
