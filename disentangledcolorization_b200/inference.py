@@ -67,6 +67,31 @@ def _fetch_np(img_path, no_resize):
     return gray[0].numpy(), ab[0].numpy(), hw
 
 
+_U8_TO_UNIT = None
+
+
+def _fetch_into(img_path, gray_out, ab_out):
+    """`fetch_data(img_path, org_size=False)` written straight into (1,256,256) / (2,256,256) float32 views of a pinned
+    batch buffer, bit-identical to it (tests/test_cli_cpu.py) but with every heavy step inside OpenCV / numpy loops that
+    release the GIL: the uint8 -> [0,1] step `np.array(rgb / 255.0, np.float32)` becomes a 256-entry table lookup of the
+    same float64-divided, float32-rounded values."""
+    import cv2
+    global _U8_TO_UNIT
+    if _U8_TO_UNIT is None:
+        _U8_TO_UNIT = np.array(np.arange(256) / 255.0, np.float32)
+    bgr = cv2.imread(img_path, cv2.IMREAD_COLOR)
+    if bgr is None:
+        raise IOError(f"cannot read image {img_path}")
+    H, W = bgr.shape[:2]
+    rgb = cv2.resize(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), (256, 256), interpolation=cv2.INTER_LINEAR)
+    lab = cv2.cvtColor(cv2.LUT(rgb, _U8_TO_UNIT), cv2.COLOR_RGB2LAB)
+    np.subtract(lab[:, :, 0], np.float32(50.0), out=gray_out[0])
+    np.divide(gray_out[0], np.float32(50.0), out=gray_out[0])
+    np.divide(lab[:, :, 1], np.float32(110.0), out=ab_out[0])
+    np.divide(lab[:, :, 2], np.float32(110.0), out=ab_out[1])
+    return (H, W)
+
+
 def _save_rgb(path, rgb):
     """PNG writer for the writer threads (cv2 releases the GIL while encoding; pixels equal PIL's Image.save)."""
     import cv2
@@ -97,24 +122,57 @@ def test_model(args):
                                       learning_pos=args.learning_pos, n_clusters=args.n_clusters,
                                       random_hint=args.random_hint, hint2regress=args.hint2regress, enhanced=True,
                                       precision=args.precision)
+    start = time.time()
     assert os.path.exists(args.checkpt), args.checkpt
     load_checkpoint(args.checkpt, net)
     print("-weight loaded successfully.")
     net = net.cuda().eval()
     net.batched_diverse = True
+    t_ready = time.time()
     dev = torch.device("cuda", torch.cuda.current_device())
     handle = _lib.Handle.get(dev.index)
     sampled_T = 2 if args.diverse else 0
     n_var = 3 if args.diverse else 1
-    start = time.time()
     n_threads = max(1, args.io_threads)
     readers = cf.ThreadPoolExecutor(n_threads)
     writers = cf.ThreadPoolExecutor(n_threads)
     window = max(2 * args.batch, 2 * n_threads)          # decoded images in flight
     metas, writes = [], []                                # per batch: [(file name, (H, W)), ...]; pending PNG writes
 
+    def batches_resized():
+        """Default mode: every image becomes 256 x 256, so image k's place (batch k // B, row k % B) is known before it is
+        decoded and the reader threads fill the pinned batch buffers themselves; the main thread only waits for a batch's
+        futures.  A ring of 5 buffer sets: 2 in the GPU pipeline, 2 being filled, 1 spare; a set is refilled only after the
+        H2D copy of its previous batch has completed (event recorded by the pipeline)."""
+        B, n, R, look = args.batch, len(img_list), 5, 2
+        nb = (n + B - 1) // B
+        sets = [dict(gray=torch.empty(B, 1, 256, 256).pin_memory(), ab=torch.empty(B, 2, 256, 256).pin_memory(), ev=None)
+                for _ in range(min(R, max(nb, 1)))]
+
+        def submit(bi):
+            st = sets[bi % len(sets)]
+            if st["ev"] is not None:
+                st["ev"].synchronize()
+            g, a = st["gray"].numpy(), st["ab"].numpy()
+            futs = []
+            for k in range(bi * B, min(n, (bi + 1) * B)):
+                print("-processing %s ..." % os.path.basename(img_list[k]))
+                futs.append(readers.submit(_fetch_into, img_list[k], g[k - bi * B], a[k - bi * B]))
+            return futs
+
+        pend = {bi: submit(bi) for bi in range(min(look, nb))}
+        for bi in range(nb):
+            if bi + look < nb:
+                pend[bi + look] = submit(bi + look)
+            hws = [f.result() for f in pend.pop(bi)]
+            st = sets[bi % len(sets)]
+            st["ev"] = torch.cuda.Event()
+            names = [os.path.splitext(os.path.basename(img_list[bi * B + i]))[0] + ".png" for i in range(len(hws))]
+            metas.append(list(zip(names, hws)))
+            yield st["gray"][:len(hws)], st["ab"][:len(hws)], st["ev"]
+
     def batches():
-        """Consecutive images of equal (padded) size, at most --batch per forward, staged in pinned memory."""
+        """--no_resize: consecutive images of equal (padded) size, at most --batch per forward, staged in pinned memory."""
         pending = collections.deque()
         it = iter(img_list)
 
@@ -158,19 +216,28 @@ def test_model(args):
                    "disco_lab2rgb_u8")
         return rgb
 
+    def _save_many(items):
+        for path, img in items:
+            _save_rgb(path, img)
+
     def on_result(i, host):
-        """host thread, batch i has landed in pinned memory: crop the padding off, hand the images to the writer threads"""
-        arr = host.numpy()
+        """host thread, batch i has landed in pinned memory: take a private copy (the slot buffer is reused two steps
+        later), crop the padding off, hand the images to the writer threads in chunks"""
+        arr = host.numpy().copy()
         B = len(metas[i])
+        items = []
         for v in range(n_var):
             for k, (name, (H, W)) in enumerate(metas[i]):
                 img = arr[v * B + k]
-                img = img[:H, :W] if args.no_resize else img
+                img = np.ascontiguousarray(img[:H, :W]) if args.no_resize else img
                 out_name = name.replace(".png", "-c%d.png" % v) if args.diverse else name
-                writes.append(writers.submit(_save_rgb, os.path.join(save_dir, out_name), np.ascontiguousarray(img)))
+                items.append((os.path.join(save_dir, out_name), img))
+        chunk = max(1, len(items) // (2 * n_threads))
+        for c in range(0, len(items), chunk):
+            writes.append(writers.submit(_save_many, items[c:c + chunk]))
 
     pipe = ColorizePipeline(net, device=dev, sampled_T=sampled_T)
-    pipe.run(batches(), post=to_rgb, on_result=on_result, keep="none")
+    pipe.run(batches() if args.no_resize else batches_resized(), post=to_rgb, on_result=on_result, keep="none")
     for w in writes:
         w.result()
     readers.shutdown()
@@ -178,7 +245,7 @@ def test_model(args):
     n_done = sum(len(m) for m in metas)
     dt = time.time() - start
     print("-processed %d imgs. consumed %f sec" % (n_done, dt))
-    return n_done, dt
+    return n_done, dt, time.time() - t_ready
 
 
 def build_parser():

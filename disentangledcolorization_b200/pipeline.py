@@ -43,7 +43,8 @@ class ColorizePipeline:
             s["ab"] = torch.empty(b, 2, h, w, device=self.dev)
             s["shape"] = shape
 
-    def _stage(self, slot, gray_host, ab_host):
+    def _stage(self, slot, gray_host, ab_host, host_free=None):
+        """`host_free` (optional torch.cuda.Event): recorded once both copies have read the pinned source buffers."""
         s = self.slots[slot]
         self._fit(s, (gray_host.shape[0], gray_host.shape[2], gray_host.shape[3]))
         if s["used"]:
@@ -52,9 +53,11 @@ class ColorizePipeline:
             s["gray"].copy_(gray_host, non_blocking=True)
             s["ab"].copy_(ab_host, non_blocking=True)
             s["ev_in"].record(self.h2d)
+            if host_free is not None:
+                host_free.record(self.h2d)
 
     def run(self, batches, on_step=None, before_step=None, on_result=None, keep="copy", post=None):
-        """batches: iterable of (gray_host, ab_host) pinned fp32 tensors (any length, shapes may change).
+        """batches: iterable of (gray_host, ab_host[, host_free_event]) pinned fp32 tensors (any length, shapes may change).
         `on_step(out_tuple)` runs on the compute stream right after each forward (e.g. the all-gather of the multi-GPU
         job); `post(out_tuple, gray_dev, ab_dev)` returns the device tensor to copy back (default: pred_colors).
 
@@ -82,13 +85,13 @@ class ColorizePipeline:
         nxt = next(it, None)
         if nxt is None:
             return results
-        self._stage(0, *nxt[:2])
+        self._stage(0, *nxt[:3])
         i = 0
         while nxt is not None:
             s = self.slots[i % self.depth]
             nxt = next(it, None)
             if nxt is not None:
-                self._stage((i + 1) % self.depth, *nxt[:2])
+                self._stage((i + 1) % self.depth, *nxt[:3])
             if i >= self.depth:
                 retire(i - self.depth)                  # this slot's previous result leaves before its host buffer is reused
                                                         # (that step finished while step i-1 was running: no bubble)

@@ -48,3 +48,21 @@ def test_bare_name_compat_modules():
         sys.path.pop(0)
         for k in ("model", "basic", "network"):
             sys.modules.pop(k, None)
+
+
+def test_fast_reader_is_bit_identical_to_fetch_data(tmp_path):
+    """The pipeline's reader (`_fetch_into`: table lookup instead of the float64 division, results written into batch
+    buffer views) feeds the network exactly what `fetch_data` (reference inference.py:23-42) feeds it."""
+    import cv2
+    from disentangledcolorization_b200 import inference
+    rng = np.random.default_rng(5)
+    for i, (h, w) in enumerate([(50, 70), (256, 256), (300, 481), (17, 9)]):
+        img = (rng.random((h, w, 3)) * 255).astype(np.uint8)
+        path = str(tmp_path / f"im{i}.png")
+        cv2.imwrite(path, img)
+        gray, ab, hw = inference.fetch_data(path, org_size=False)
+        g = np.full((1, 256, 256), np.nan, np.float32)
+        a = np.full((2, 256, 256), np.nan, np.float32)
+        hw2 = inference._fetch_into(path, g, a)
+        assert hw2 == hw
+        assert np.array_equal(g, gray[0].numpy()) and np.array_equal(a, ab[0].numpy())
