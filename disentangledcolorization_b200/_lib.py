@@ -19,7 +19,8 @@ EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create"
            "disco_attention", "disco_kmeans_anchor", "disco_token_labels", "disco_set_tensor_core",
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
            "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows",
-           "disco_encoder_stack", "disco_encoder_stack_pack", "disco_encoder_stack_scratch_elems", "disco_segnet_head", "disco_lab2rgb_u8"]
+           "disco_encoder_stack", "disco_encoder_stack_pack", "disco_encoder_stack_scratch_elems", "disco_segnet_head", "disco_lab2rgb_u8", "disco_ce_rebalance",
+           "disco_spixel_recon_loss", "disco_encode_ab2ind"]
 
 
 class ConvSrc(C.Structure):
@@ -89,6 +90,9 @@ def load():
     lib.disco_encoder_stack.argtypes = [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 3
     lib.disco_segnet_head.argtypes = [C.c_void_p] * 8 + [C.c_float] + [C.c_int] * 3 + [C.c_void_p] * 3
     lib.disco_lab2rgb_u8.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p] * 2
+    lib.disco_encode_ab2ind.argtypes = [C.c_void_p] * 3 + [C.c_int] * 2 + [C.c_void_p] * 2
+    lib.disco_ce_rebalance.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_void_p] * 4
+    lib.disco_spixel_recon_loss.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.disco_host_choice_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)] + [C.c_int] * 5 + [C.c_void_p]
     lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2

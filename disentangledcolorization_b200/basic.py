@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .cielab import Q_TO_AB
+from .cielab import Q_TO_AB, class_weights
 
 
 def tensor2array(tensors):
@@ -91,6 +91,22 @@ class ColorLabel:
 
     def __init__(self, lambda_=0.5, device="cuda"):
         self.q_to_ab = torch.from_numpy(Q_TO_AB.copy()).to(device)
+        self.weights = torch.from_numpy(class_weights(lambda_)).to(device)        # float32, like the reference (:153-157)
+
+    def get_classweights(self, batch_gt_indx):
+        """models/basic.py:173-175."""
+        return self.weights.to(batch_gt_indx.device)[batch_gt_indx]
+
+    def encode_ab2ind(self, batch_ab, neighbours=5, sigma=5.0):
+        """models/basic.py:177-194: soft 313-way code (5 nearest bins, Gaussian weights); (N,2,h,w) -> (N,313,h,w)."""
+        if neighbours != 5 or sigma != 5.0:
+            raise _lib.DiscoError("encode_ab2ind is built for neighbours=5, sigma=5.0 (the only values the reference uses)")
+        B, _, h, w = batch_ab.shape
+        handle, stream = _ctx(batch_ab)
+        q = torch.empty(B, 313, h, w, dtype=torch.float32, device=batch_ab.device)
+        _lib.check(handle.lib.disco_encode_ab2ind(handle.h, _p(batch_ab.float().contiguous()), _p(self.q_to_ab.to(batch_ab.device)),
+                                                  B, h * w, _p(q), stream), "disco_encode_ab2ind")
+        return q
 
     def decode_ind2ab(self, batch_q, T=0.38):
         """T-th most probable bin -> ab/110 (integer T) or annealed mean (fractional T); host-side glue on

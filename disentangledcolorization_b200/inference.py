@@ -95,7 +95,9 @@ def _fetch_into(img_path, gray_out, ab_out):
 def _save_rgb(path, rgb):
     """PNG writer for the writer threads (cv2 releases the GIL while encoding; pixels equal PIL's Image.save)."""
     import cv2
-    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)):
+    # compression level 1: the pixels are what the reference's PIL save stores; a lighter zlib level keeps 16 writer
+    # threads ahead of the GPU
+    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR), [cv2.IMWRITE_PNG_COMPRESSION, 1]):
         raise IOError(f"cannot write {path}")
 
 

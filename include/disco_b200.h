@@ -251,6 +251,27 @@ int disco_token_labels(disco_handle* h, int mode, const float* src, const float*
 int disco_token_sample3(disco_handle* h, const float* logits, const float* q_to_ab, int batch, int S,
                         int32_t* labels3, float* colors3, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-side losses (BASELINE config 5; first slice of SURVEY 8f N3/N4 -- the conv / transformer backward is not built).
+ * disco_ce_rebalance: one token-level term of AnchorColorProbLoss.__call__ (models/loss.py:59-76): nn.CrossEntropyLoss
+ * (mean, ignore_index -1) of a [B,313,S] logit map against hard labels, and d loss / d logits as autograd delivers it
+ * through basic.RebalanceLoss (models/basic.py:120-134): (softmax - onehot) / n_valid * token_weights[token].
+ *   logits fp32 [B,313,S]; labels int32 [B*S] (disco_token_labels mode 1 of the pooled GT colours, -1 = ignored);
+ *   token_weights fp32 [B*S] (data['class_weight'] = ColorLabel.get_classweights(labels), models/basic.py:173-175);
+ *   token_loss fp32 [B*S] (out);
+ *   loss_out fp32 [2] = {mean CE, n_valid}; dlogits fp32 [B,313,S] or NULL
+ * disco_spixel_recon_loss: SPixelLoss.__call__ (models/loss.py:17-30) after recon = upfeat(poolfeat(target, prob), prob):
+ *   loss_out[0] = mean_pixels ||recon - target||_2 over channels [0, C-2), loss_out[1] = the same over the last 2 channels
+ *   (the caller forms 10 * feat + 0.003 * pos / kernel_size); partial: fp32 workspace [n_partial][2]
+ * ------------------------------------------------------------------------------------------- */
+ /* ColorLabel.encode_ab2ind (models/basic.py:177-194): ab fp32 [B,2,S] (ab/110) -> soft code q fp32 [B,313,S]
+  * (5 nearest bins, Gaussian sigma 5, normalised) */
+int disco_encode_ab2ind(disco_handle* h, const float* ab, const float* q_to_ab, int batch, int S, float* q, void* stream);
+int disco_ce_rebalance(disco_handle* h, const float* logits, const int32_t* labels, const float* token_weights, int batch, int S,
+                       float* token_loss, float* loss_out, float* dlogits, void* stream);
+int disco_spixel_recon_loss(disco_handle* h, const float* recon, const float* target, int batch, int C, int H, int W,
+                            float* partial, int n_partial, float* loss_out, void* stream);
+
 /* Lab -> sRGB uint8, the image the CLI saves (main/colorizer/inference.py:119-127 + utils/util.py:91-106:
  * L = (gray + 1) * 50, ab * 110, cv2.cvtColor(COLOR_LAB2RGB) on float32, * 255, astype(uint8)).
  *   gray fp32 [B,1,H,W], ab fp32 [B,2,H,W] (normalised, as the forward returns pred_colors);

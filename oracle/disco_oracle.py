@@ -376,3 +376,53 @@ def forward(sd, gray, ab, n_clusters=8, sampled_T=0, sp=16, hint_mask=None, stag
     if stages is not None:
         stages.update(feats=feats, tokens=tokens, sizes=sizes, enc=enc, labels=labels, dec=dec, full=full)
     return pal_logit, ref_logit, pred, affinity, sampled, hint_mask
+
+
+# ----------------------------------------------------------------------------------------------
+# training-side losses on the forward's outputs (config 5; models/loss.py:12-87, models/basic.py:120-134,153-175)
+# ----------------------------------------------------------------------------------------------
+def class_weights(lambda_=0.5):
+    """ColorLabel.weights (models/basic.py:153-157) from the gamut prior (utils/gamut_probs.npy)."""
+    from disentangledcolorization_b200.cielab import gamut_prior  # data table only
+    prior = torch.from_numpy(gamut_prior().astype(np.float32))      # ABGamut.DTYPE = float32 (utils/cielab.py:8-11)
+    uniform = torch.zeros_like(prior)
+    uniform[prior > 0] = 1 / (prior > 0).sum().type_as(uniform)
+    w = 1 / ((1 - lambda_) * prior + lambda_ * uniform)
+    return w / torch.sum(prior * w)
+
+
+class _Rebalance(torch.autograd.Function):
+    """basic.RebalanceLoss (models/basic.py:120-134): identity forward, gradient multiplied by the weights."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(w)
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        return g * w, None
+
+
+def anchor_color_prob_loss(pal_logit, ref_logit, target_label, class_weight):
+    """AnchorColorProbLoss.__call__ with hint2regress=False, enhanced=False (models/loss.py:59-87): returns the dict."""
+    N, C, H, W = target_label.shape
+    labels = target_label.permute(0, 2, 3, 1).contiguous().view(N * H * W)
+    out = {}
+    for key, logit in (("palLoss", pal_logit), ("refLoss", ref_logit)):
+        probs = _Rebalance.apply(logit, class_weight).permute(0, 2, 3, 1).contiguous().view(N * H * W, -1)
+        out[key] = F.cross_entropy(probs, labels, ignore_index=-1)
+    out["recLoss"] = torch.zeros_like(out["palLoss"])
+    out["totalLoss"] = out["palLoss"] + out["refLoss"] + out["recLoss"]
+    return out
+
+
+def spixel_loss(prob, feat, k=16):
+    """SPixelLoss.__call__ (models/loss.py:17-30)."""
+    pooled, _ = poolfeat(feat, prob, k)
+    recon = upfeat(pooled, prob, k)
+    d = recon - feat
+    f = torch.norm(d[:, :-2], p=2, dim=1).mean()
+    p_ = torch.norm(d[:, -2:], p=2, dim=1).mean() / k
+    return {"totalLoss": 10 * f + 0.003 * p_, "featLoss": f, "posLoss": p_}

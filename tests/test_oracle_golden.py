@@ -66,3 +66,28 @@ def test_state_dict_schema_matches_reference():
     assert len(mine) == len(ref) == 461
     for k, s, p in ref:
         assert mine[k] == (s, p), k
+
+
+def test_oracle_losses_match_reference_fixture():
+    """The oracle's restatement of AnchorColorProbLoss / RebalanceLoss / class weights / SPixelLoss / encode_ab2ind against
+    tests/golden/loss_terms.npz, generated with the unmodified reference by oracle/make_golden_loss.py."""
+    import numpy as np
+    import torch
+    import disco_oracle as O
+    g = load_golden("loss_terms")
+    w = O.class_weights()
+    assert np.allclose(w.numpy(), g["weights_table"], rtol=1e-6, atol=0)
+    soft = O.encode_ab2ind(torch.from_numpy(g["spix"]))
+    assert np.abs(soft.numpy() - g["soft"]).max() < 1e-6
+    labels = soft.max(dim=1, keepdim=True)[1]
+    assert np.array_equal(labels.numpy(), g["labels"])
+    cw = w[labels]
+    assert np.allclose(cw.numpy(), g["class_weight"])
+    pal = torch.from_numpy(g["pal"]).requires_grad_(True)
+    ref = torch.from_numpy(g["ref"]).requires_grad_(True)
+    d = O.anchor_color_prob_loss(pal, ref, labels, cw.float())
+    d["totalLoss"].backward()
+    assert abs(d["palLoss"].item() - float(g["palLoss"])) < 1e-5 and abs(d["refLoss"].item() - float(g["refLoss"])) < 1e-5
+    assert np.abs(pal.grad.numpy() - g["pal_grad"]).max() < 1e-6 and np.abs(ref.grad.numpy() - g["ref_grad"]).max() < 1e-6
+    sp = O.spixel_loss(torch.from_numpy(g["prob"]), torch.from_numpy(g["feat"]), 16)
+    assert abs(sp["totalLoss"].item() - float(g["sp_total"])) < 1e-4 and abs(sp["posLoss"].item() - float(g["sp_pos"])) < 1e-6
