@@ -85,19 +85,21 @@ def _fetch_into(img_path, gray_out, ab_out):
     H, W = bgr.shape[:2]
     rgb = cv2.resize(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), (256, 256), interpolation=cv2.INTER_LINEAR)
     lab = cv2.cvtColor(cv2.LUT(rgb, _U8_TO_UNIT), cv2.COLOR_RGB2LAB)
-    np.subtract(lab[:, :, 0], np.float32(50.0), out=gray_out[0])
+    L, A, B = cv2.split(lab)                                  # contiguous planes: the arithmetic below runs at memcpy speed
+    np.subtract(L, np.float32(50.0), out=gray_out[0])
     np.divide(gray_out[0], np.float32(50.0), out=gray_out[0])
-    np.divide(lab[:, :, 1], np.float32(110.0), out=ab_out[0])
-    np.divide(lab[:, :, 2], np.float32(110.0), out=ab_out[1])
+    np.divide(A, np.float32(110.0), out=ab_out[0])
+    np.divide(B, np.float32(110.0), out=ab_out[1])
     return (H, W)
 
 
 def _save_rgb(path, rgb):
     """PNG writer for the writer threads (cv2 releases the GIL while encoding; pixels equal PIL's Image.save)."""
     import cv2
-    # compression level 1: the pixels are what the reference's PIL save stores; a lighter zlib level keeps 16 writer
-    # threads ahead of the GPU
-    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR), [cv2.IMWRITE_PNG_COMPRESSION, 1]):
+    # zlib level 1 with the RLE strategy: the pixels are what the reference's PIL save stores (level 6: ~3x the CPU time
+    # per image); PNG encoding is what bounds the CLI once the forward runs on the GPU (DESIGN section 5.4)
+    if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR),
+                       [cv2.IMWRITE_PNG_COMPRESSION, 1, cv2.IMWRITE_PNG_STRATEGY, cv2.IMWRITE_PNG_STRATEGY_RLE]):
         raise IOError(f"cannot write {path}")
 
 
@@ -136,6 +138,9 @@ def test_model(args):
     sampled_T = 2 if args.diverse else 0
     n_var = 3 if args.diverse else 1
     n_threads = max(1, args.io_threads)
+    import cv2
+    cv_threads = cv2.getNumThreads()
+    cv2.setNumThreads(1)                                  # parallelism comes from the reader / writer pools, not from inside OpenCV
     readers = cf.ThreadPoolExecutor(n_threads)
     writers = cf.ThreadPoolExecutor(n_threads)
     window = max(2 * args.batch, 2 * n_threads)          # decoded images in flight
@@ -244,6 +249,7 @@ def test_model(args):
         w.result()
     readers.shutdown()
     writers.shutdown()
+    cv2.setNumThreads(cv_threads)
     n_done = sum(len(m) for m in metas)
     dt = time.time() - start
     print("-processed %d imgs. consumed %f sec" % (n_done, dt))
