@@ -205,24 +205,29 @@ __global__ void __launch_bounds__(256) upfeat_kernel(const float* __restrict__ t
   }
   __syncthreads();
   const int x = tid >> 4, cg = tid & 15;
-  float t[9][4];
+  f32x2 t2[9][2];                    // the 3x3 neighbourhood's tokens, this thread's 4 channels, as packed fp32 pairs (FFMA2)
 #pragma unroll
-  for (int k = 0; k < 9; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[k][j] = Tk[k][cg * 4 + j];
+  for (int k = 0; k < 9; ++k) {
+    t2[k][0] = pack2(Tk[k][cg * 4 + 0], Tk[k][cg * 4 + 1]);
+    t2[k][1] = pack2(Tk[k][cg * 4 + 2], Tk[k][cg * 4 + 3]);
+  }
   T* base = out + (((size_t)n * H + cy * SP) * W + cx * SP + x) * 64 + cg * 4;
 #pragma unroll 4
   for (int y = 0; y < SP; ++y) {
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    f32x2 o01 = pack2(0.f, 0.f), o23 = pack2(0.f, 0.f);
     const float4 p0 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP);
     const float4 p1 = *reinterpret_cast<const float4*>(Pk + (y * SP + x) * PKP + 4);
     const float p8 = Pk[(y * SP + x) * PKP + 8];
     const float pv[9] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p8};
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = fmaf(t[k][j], pv[k], o[j]);
+      const f32x2 pp = pack2(pv[k], pv[k]);
+      o01 = ffma2(t2[k][0], pp, o01);
+      o23 = ffma2(t2[k][1], pp, o23);
     }
+    float o[4];
+    unpack2(o01, o[0], o[1]);
+    unpack2(o23, o[2], o[3]);
     st4<T>(base + (size_t)y * W * 64, o);
   }
 }
