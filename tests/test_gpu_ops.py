@@ -168,6 +168,40 @@ def test_poolfeat_upfeat_match_oracle():
     assert (rt.cpu() - tok).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 48, 80), (1, 16, 16), (3, 64, 64)], ids=lambda v: str(v))
+def test_poolfeat_bf16_tensor_core_kernel_matches_oracle(B, H, W):
+    """disco_poolfeat on bf16 features (the tensor-core kernel: affinity split hi + lo, mma.sync) against the oracle's
+    poolfeat / get_spixel_size on the same bf16-rounded features: the split product is fp32-grade, so the tolerance is
+    the fp32 one.  Includes a hard one-hot affinity (ties in the hard mass) and borders."""
+    import disco_oracle as O
+    from disentangledcolorization_b200 import _lib
+    h = _handle()
+    g = torch.Generator().manual_seed(3 + H)
+    feat = torch.relu(torch.randn(B, 64, H, W, generator=g)).to(torch.bfloat16)
+    ab = torch.rand(B, 2, H, W, generator=g) - 0.5
+    prob = torch.softmax(torch.randn(B, 9, H, W, generator=g) * 2, 1)
+    prob[0, :, :8] = 0
+    prob[0, 4, :8] = 1                                   # rows with a one-hot assignment
+    hh, ww, S = H // 16, W // 16, (H // 16) * (W // 16)
+    f32 = dict(dtype=torch.float32, device="cuda")
+    feats = feat.permute(0, 2, 3, 1).contiguous().cuda()
+    partial = torch.empty(B, hh, ww, 9, 68, **f32)
+    tokens, spix = torch.empty(B, S, 64, **f32), torch.empty(B, 2, hh, ww, **f32)
+    conf, sizes = torch.empty(B, S, **f32), torch.empty(B, S, **f32)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    ab_d, prob_d = ab.cuda(), prob.cuda()                # keep the device copies alive across the asynchronous launch
+    _lib.check(h.lib.disco_poolfeat(h.h, _lib.BF16, p(feats), p(ab_d), p(prob_d), B, H, W, 64, p(partial), p(tokens),
+                                    p(spix), p(conf), p(sizes), _stream()), "disco_poolfeat")
+    torch.cuda.synchronize()
+    want, mass = O.poolfeat(torch.cat([feat.float(), ab], 1), prob, 16)
+    got = tokens.view(B, hh, ww, 64).permute(0, 3, 1, 2).cpu()
+    scale = max(1.0, float(want.abs().max()))
+    assert float((got - want[:, :64]).abs().max()) < 2e-5 * scale
+    assert float((spix.cpu() - want[:, 64:]).abs().max()) < 1e-5
+    assert float((conf.view(B, 1, hh, ww).cpu() - mass).abs().max()) < 3e-6          # affinity split hi + lo: 2^-17 relative
+    assert float((sizes.view(B, 1, hh, ww).cpu() - O.get_spixel_size(prob, 16)).abs().max()) < 1e-6
+
+
 def test_encoder_stack_matches_oracle(synth_sd):
     import disco_oracle as O
     from disentangledcolorization_b200.engine import Engine
