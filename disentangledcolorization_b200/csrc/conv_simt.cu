@@ -7,6 +7,7 @@
 // x 64 output channels per CTA, K stepped by (source, tap, 16 input channels) through shared memory,
 // 4x4 register micro-tiles.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -268,6 +269,124 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cin == 1 -> 64 channels on tensor cores (repnet.conv1_2.0, reference models/network.py:152).  The CUDA-core kernel above
+// is issue-bound (r2a capture: 63 % of the issue slots, 36 % of the HBM peak): 9 x 64 FMAs + the epilogue per pixel.
+// As a GEMM the layer is [pixels x 32] x [32 x 64] with the K axis holding, per pixel, the nine L-channel taps split into
+// bf16 hi + lo against the weights split the same way (g_hi w_hi + g_lo w_hi + g_hi w_lo: fp32-grade products; the
+// L channel is fp32 and must not be rounded to bf16) and two constant-one columns that carry the bias (hi, lo):
+//   k = 8 s + j;  s = 0: g_hi[tap j] x w_hi[j];  s = 1: g_lo[tap j] x w_hi[j];  s = 2: g_hi[tap j] x w_lo[j]   (taps 0..7)
+//   s = 3: j = 0: g_hi[8] x w_hi[8];  1: g_lo[8] x w_hi[8];  2: g_hi[8] x w_lo[8];  3: 1 x b_hi;  4: 1 x b_lo;  5..7: 0
+// so that in the m16n8k16 A fragment thread t needs exactly the taps 2t, 2t+1 (and 8): 16 MMAs per 16 pixels x 64 channels
+// instead of 144 FFMA2 warp instructions.  The B operand (32 x 64, 32 registers) is built once per thread.
+// One warp = 16 consecutive pixels of a row; the bf16 tile is staged in a private shared-memory patch and written out as
+// whole 128-byte pixel rows.  grid = (ceil(W / 64), ceil(H / 16), B), 256 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1M_TW = 64, C1M_TH = 16;
+__device__ __forceinline__ void c1m_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffff0000u);        // truncation: hi is exactly a bf16, lo = x - hi is exact in fp32
+  lo = x - hi;
+}
+__device__ __forceinline__ uint32_t c1m_pack(float a, float b) {   // bf16x2, element a in the low half (round to nearest)
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void c1m_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) conv_c1_mma_kernel(const float* __restrict__ gray, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ ps,
+                                                             const float* __restrict__ pb, int H, int W, int act, float slope,
+                                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ float sg[(C1M_TH + 2) * (C1M_TW + 2)];
+  __shared__ __align__(16) uint8_t patch[8][16 * 144];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int x0 = blockIdx.x * C1M_TW, y0 = blockIdx.y * C1M_TH, n = blockIdx.z;
+  {
+    const float* gi = gray + (size_t)n * H * W;
+    for (int i = tid; i < (C1M_TH + 2) * (C1M_TW + 2); i += 256) {
+      const int ry = i / (C1M_TW + 2), rx = i - ry * (C1M_TW + 2);
+      const int y = y0 - 1 + ry, x = x0 - 1 + rx;
+      sg[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(gi + (size_t)y * W + x) : 0.f;
+    }
+  }
+  // ---- B fragments: b[ks][j][0] = B[k = 16 ks + 2t, +1][n = 8j + g], b[ks][j][1] = B[k = 16 ks + 8 + 2t, +1][n]
+  uint32_t bfr[2][8][2];
+  {
+    auto whi = [&](int tap, int co) { float hi, lo; c1m_split(w[tap * 64 + co], hi, lo); return hi; };
+    auto wlo = [&](int tap, int co) { float hi, lo; c1m_split(w[tap * 64 + co], hi, lo); return lo; };
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = 8 * j + g;
+      float bh, bl;
+      c1m_split(bias[co], bh, bl);
+      // slot s = k / 8: ks 0 holds slots 0 (reg 0) and 1 (reg 1); ks 1 holds slots 2 (reg 0) and 3 (reg 1)
+      bfr[0][j][0] = c1m_pack(whi(2 * t, co), whi(2 * t + 1, co));
+      bfr[0][j][1] = bfr[0][j][0];
+      bfr[1][j][0] = c1m_pack(wlo(2 * t, co), wlo(2 * t + 1, co));
+      const float s3a = t == 0 ? whi(8, co) : (t == 1 ? wlo(8, co) : (t == 2 ? bl : 0.f));
+      const float s3b = t == 0 ? whi(8, co) : (t == 1 ? bh : 0.f);
+      bfr[1][j][1] = c1m_pack(s3a, s3b);
+    }
+  }
+  float sc[8][2], sh[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sc[j][e] = ps ? ps[8 * j + 2 * t + e] : 1.f;
+      sh[j][e] = pb ? pb[8 * j + 2 * t + e] : 0.f;
+    }
+  __syncthreads();
+  // taps 2t, 2t+1 and 8 as offsets into the staged tile
+  const int o0 = ((2 * t) / 3) * (C1M_TW + 2) + (2 * t) % 3, o1 = ((2 * t + 1) / 3) * (C1M_TW + 2) + (2 * t + 1) % 3;
+  const int o8 = 2 * (C1M_TW + 2) + 2;
+  uint8_t* mp = patch[warp];
+  for (int mt = warp; mt < (C1M_TW / 16) * C1M_TH; mt += 8) {
+    const int ry = mt >> 2, rx = (mt & 3) * 16;             // tile row, first pixel of the 16-pixel run
+    uint32_t a[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {                          // fragment rows g and g + 8
+      const float* p = sg + ry * (C1M_TW + 2) + rx + g + 8 * r;
+      float h0, l0, h1, l1, h8, l8;
+      c1m_split(p[o0], h0, l0);
+      c1m_split(p[o1], h1, l1);
+      c1m_split(p[o8], h8, l8);
+      const uint32_t s0 = c1m_pack(h0, h1);                 // exact: both are bf16 values
+      const uint32_t s1 = c1m_pack(l0, l1);
+      const uint32_t s3 = t == 0 ? c1m_pack(h8, l8) : (t == 1 ? c1m_pack(h8, 1.0f) : (t == 2 ? c1m_pack(1.0f, 0.f) : 0u));
+      a[0][r] = s0; a[0][2 + r] = s1;                       // k-step 0: slots 0 | 1
+      a[1][r] = s0; a[1][2 + r] = s3;                       // k-step 1: slots 2 | 3
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      c1m_mma(acc[j], a[0][0], a[0][1], a[0][2], a[0][3], bfr[0][j][0], bfr[0][j][1]);
+      c1m_mma(acc[j], a[1][0], a[1][1], a[1][2], a[1][3], bfr[1][j][0], bfr[1][j][1]);
+    }
+    __syncwarp();                                           // the previous tile's copy-out has left the patch
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = apply_act(acc[j][e], act, slope) * sc[j][e & 1] + sh[j][e & 1];
+      *reinterpret_cast<uint32_t*>(mp + g * 144 + 16 * j + 4 * t) = c1m_pack(v[0], v[1]);
+      *reinterpret_cast<uint32_t*>(mp + (g + 8) * 144 + 16 * j + 4 * t) = c1m_pack(v[2], v[3]);
+    }
+    __syncwarp();
+    const int y = y0 + ry;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = lane + 32 * r, px = i >> 3, pc = i & 7, x = x0 + rx + px;
+      if (y < H && x < W)
+        *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * 64 + pc * 8) = *reinterpret_cast<const uint4*>(mp + px * 144 + pc * 16);
+    }
+  }
+}
+
 }  // namespace
 
 int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
@@ -278,6 +397,14 @@ int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st)
   if (d->dtype == DISCO_BF16 && d->kind == DISCO_CONV3 && d->n_src == 1 && d->src[0].C == 1 && d->src[0].is_f32 &&
       d->stride == 1 && !d->src[0].up2 && d->head == DISCO_HEAD_NONE && !d->residual && d->Cout % 4 == 0 &&
       256 % (d->Cout / 4) == 0 && d->batch * ((d->Ho + 15) / 16) <= 65535 && (long long)d->Ho * d->Wo * (d->Cout / 4) < (1ll << 31)) {
+    if (d->Cout == 64 && d->batch <= 65535 && (getenv("DISCO_C1_MMA") == nullptr || getenv("DISCO_C1_MMA")[0] != '0')) {
+      dim3 grid((d->Wo + C1M_TW - 1) / C1M_TW, (d->Ho + C1M_TH - 1) / C1M_TH, d->batch);
+      conv_c1_mma_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(d->src[0].ptr),
+                                               reinterpret_cast<const float*>(d->weights) + d->src[0].w_off, d->bias, d->post_scale,
+                                               d->post_shift, d->Ho, d->Wo, d->act, d->slope, reinterpret_cast<__nv_bfloat16*>(d->out));
+      DISCO_LAUNCH_CHECK(h);
+      return DISCO_OK;
+    }
     const int tpp = d->Cout / 4, px_per_block = (256 / tpp) * 4;
     const int rows = d->batch * d->Ho;
     const int gx = (d->Wo + px_per_block - 1) / px_per_block;

@@ -137,6 +137,29 @@ def test_heads_fp32():
     assert (out - ref).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("B,H,W,post", [(2, 32, 48, False), (1, 16, 16, True), (1, 48, 80, True), (3, 20, 70, False)], ids=str)
+def test_conv_cin1_cout64_tensor_core_kernel(B, H, W, post):
+    """Cin = 1 -> 64 channels on tensor cores (conv_c1_mma_kernel: L-channel taps and weights split hi + lo, bias through
+    a constant-one column): the products are fp32-grade, so the only error against torch fp32 is the bf16 rounding of the
+    stored output.  Ragged widths (not a multiple of the 64-pixel tile), post-activation affine, image borders."""
+    import torch.nn.functional as F
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 100 + H)
+    gray = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    w = torch.randn(64, 1, 3, 3, generator=g) * 0.4
+    b = torch.randn(64, generator=g) * 0.2
+    ps, pb = (torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1) if post else (None, None)
+    out = _conv_call(_lib.BF16, _lib.CONV3, 1, [(gray.permute(0, 2, 3, 1), 0, 1)], [w], b, 64, H, W, act=_lib.ACT_LRELU, slope=0.2,
+                     post=(ps, pb) if post else None)
+    ref = F.leaky_relu(F.conv2d(gray, w, b, padding=1), 0.2)
+    if post:
+        ref = ref * ps.view(1, -1, 1, 1) + pb.view(1, -1, 1, 1)
+    ref = _nhwc(ref)
+    err = (out - ref).abs()
+    assert float((err / (ref.abs() + 1e-2)).max()) < 2.0 ** -8 + 1e-3       # one bf16 rounding of the result
+    assert float((out - ref.to(torch.bfloat16).float()).abs().max()) <= float(ref.abs().max()) * 2.0 ** -7   # at most 1 ulp off
+
+
 def test_conv_rejects_bad_descriptor():
     from disentangledcolorization_b200 import _lib
     h = _handle()
