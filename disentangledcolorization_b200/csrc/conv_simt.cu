@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const float* __restrict
 // so that in the m16n8k16 A fragment thread t needs exactly the taps 2t, 2t+1 (and 8): 16 MMAs per 16 pixels x 64 channels
 // instead of 144 FFMA2 warp instructions.  The B operand (32 x 64, 32 registers) is built once per thread.
 // One warp = 16 consecutive pixels of a row; the bf16 tile is staged in a private shared-memory patch and written out as
-// whole 128-byte pixel rows.  grid = (ceil(W / 64), ceil(H / 16), B), 256 threads.
+// whole 128-byte pixel rows.  Persistent CTAs (2 per SM) loop over 64 x 16 pixel tiles so that the B-operand set-up (about
+// 60 dependent loads per thread) is paid once per CTA, not once per tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int C1M_TW = 64, C1M_TH = 16;
 __device__ __forceinline__ void c1m_split(float x, float& hi, float& lo) {
@@ -298,20 +299,13 @@ __device__ __forceinline__ void c1m_mma(float (&c)[4], uint32_t a0, uint32_t a1,
 
 __global__ void __launch_bounds__(256, 2) conv_c1_mma_kernel(const float* __restrict__ gray, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ ps,
-                                                             const float* __restrict__ pb, int H, int W, int act, float slope,
+                                                             const float* __restrict__ pb, int B, int H, int W, int act, float slope,
                                                              __nv_bfloat16* __restrict__ out) {
   __shared__ float sg[(C1M_TH + 2) * (C1M_TW + 2)];
   __shared__ __align__(16) uint8_t patch[8][16 * 144];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int x0 = blockIdx.x * C1M_TW, y0 = blockIdx.y * C1M_TH, n = blockIdx.z;
-  {
-    const float* gi = gray + (size_t)n * H * W;
-    for (int i = tid; i < (C1M_TH + 2) * (C1M_TW + 2); i += 256) {
-      const int ry = i / (C1M_TW + 2), rx = i - ry * (C1M_TW + 2);
-      const int y = y0 - 1 + ry, x = x0 - 1 + rx;
-      sg[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(gi + (size_t)y * W + x) : 0.f;
-    }
-  }
+  const int tiles_x = (W + C1M_TW - 1) / C1M_TW, tiles_y = (H + C1M_TH - 1) / C1M_TH;
+  const int n_tiles = tiles_x * tiles_y * B;
   // ---- B fragments: b[ks][j][0] = B[k = 16 ks + 2t, +1][n = 8j + g], b[ks][j][1] = B[k = 16 ks + 8 + 2t, +1][n]
   uint32_t bfr[2][8][2];
   {
@@ -339,11 +333,23 @@ __global__ void __launch_bounds__(256, 2) conv_c1_mma_kernel(const float* __rest
       sc[j][e] = ps ? ps[8 * j + 2 * t + e] : 1.f;
       sh[j][e] = pb ? pb[8 * j + 2 * t + e] : 0.f;
     }
-  __syncthreads();
   // taps 2t, 2t+1 and 8 as offsets into the staged tile
   const int o0 = ((2 * t) / 3) * (C1M_TW + 2) + (2 * t) % 3, o1 = ((2 * t + 1) / 3) * (C1M_TW + 2) + (2 * t + 1) % 3;
   const int o8 = 2 * (C1M_TW + 2) + 2;
   uint8_t* mp = patch[warp];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int n = tile / (tiles_x * tiles_y), tr = tile - n * (tiles_x * tiles_y);
+  const int y0 = (tr / tiles_x) * C1M_TH, x0 = (tr % tiles_x) * C1M_TW;
+  __syncthreads();                                          // every warp is done with the previous tile's L-channel patch
+  {
+    const float* gi = gray + (size_t)n * H * W;
+    for (int i = tid; i < (C1M_TH + 2) * (C1M_TW + 2); i += 256) {
+      const int ry = i / (C1M_TW + 2), rx = i - ry * (C1M_TW + 2);
+      const int y = y0 - 1 + ry, x = x0 - 1 + rx;
+      sg[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(gi + (size_t)y * W + x) : 0.f;
+    }
+  }
+  __syncthreads();
   for (int mt = warp; mt < (C1M_TW / 16) * C1M_TH; mt += 8) {
     const int ry = mt >> 2, rx = (mt & 3) * 16;             // tile row, first pixel of the 16-pixel run
     uint32_t a[2][4];
@@ -385,6 +391,7 @@ __global__ void __launch_bounds__(256, 2) conv_c1_mma_kernel(const float* __rest
         *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * 64 + pc * 8) = *reinterpret_cast<const uint4*>(mp + px * 144 + pc * 16);
     }
   }
+  }
 }
 
 }  // namespace
@@ -398,10 +405,12 @@ int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st)
       d->stride == 1 && !d->src[0].up2 && d->head == DISCO_HEAD_NONE && !d->residual && d->Cout % 4 == 0 &&
       256 % (d->Cout / 4) == 0 && d->batch * ((d->Ho + 15) / 16) <= 65535 && (long long)d->Ho * d->Wo * (d->Cout / 4) < (1ll << 31)) {
     if (d->Cout == 64 && d->batch <= 65535 && (getenv("DISCO_C1_MMA") == nullptr || getenv("DISCO_C1_MMA")[0] != '0')) {
-      dim3 grid((d->Wo + C1M_TW - 1) / C1M_TW, (d->Ho + C1M_TH - 1) / C1M_TH, d->batch);
+      const long long tiles = (long long)((d->Wo + C1M_TW - 1) / C1M_TW) * ((d->Ho + C1M_TH - 1) / C1M_TH) * d->batch;
+      const int grid = (int)(tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count);
       conv_c1_mma_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(d->src[0].ptr),
                                                reinterpret_cast<const float*>(d->weights) + d->src[0].w_off, d->bias, d->post_scale,
-                                               d->post_shift, d->Ho, d->Wo, d->act, d->slope, reinterpret_cast<__nv_bfloat16*>(d->out));
+                                               d->post_shift, d->batch, d->Ho, d->Wo, d->act, d->slope,
+                                               reinterpret_cast<__nv_bfloat16*>(d->out));
       DISCO_LAUNCH_CHECK(h);
       return DISCO_OK;
     }
