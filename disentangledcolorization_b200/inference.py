@@ -97,7 +97,7 @@ def _save_rgb(path, rgb):
     """PNG writer for the writer threads (cv2 releases the GIL while encoding; pixels equal PIL's Image.save)."""
     import cv2
     # zlib level 1 with the RLE strategy: the pixels are what the reference's PIL save stores (level 6: ~3x the CPU time
-    # per image); PNG encoding is what bounds the CLI once the forward runs on the GPU (DESIGN section 5.4)
+    # per image); PNG encoding is what bounds the CLI once the forward runs on the GPU (DESIGN section 5.3)
     if not cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR),
                        [cv2.IMWRITE_PNG_COMPRESSION, 1, cv2.IMWRITE_PNG_STRATEGY, cv2.IMWRITE_PNG_STRATEGY_RLE]):
         raise IOError(f"cannot write {path}")

@@ -38,3 +38,30 @@ def test_perop_table_matches_the_reference_flop_count():
     assert abs(conv_flops / 64 / 1e9 - 254.93) < 0.5
     executed = sum(v["executed_flops"] for v in d["per_op"].values())
     assert executed < conv_flops          # up-sampled layers run as 2x2-tap parity phases
+
+
+def test_round2_evidence_is_committed_and_consistent():
+    """profiles/r2_*: the bench line carries the round-2 keys, the per-op table still reproduces the reference's conv FLOPs
+    (the fused SpixelNet head counts its three layers), and the SASS tally shows tcgen05 + TMA + mma.sync."""
+    line = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_line.json")))
+    for key in ("parity_check", "gpu_eager_baseline", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["parity_check"]["ok"] and line["parity_check"]["vs_cpu_oracle_ok"]
+    r = line["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "whole_step" in r and "config4" in r
+    assert line["gpu_eager_baseline"]["fp32_tf32conv"]["speedup_ours_over_it"] > 1
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_perop_bench.json")))
+    conv_flops = sum(v["flops"] for v in d["per_op"].values())
+    assert abs(conv_flops / 64 / 1e9 - 254.93) < 0.5
+    assert "segnet.net.conv0a+conv0b+conv1a" in d["per_op"]
+    sass = open(os.path.join(ROOT, "profiles", "sass_opcodes.md")).read()
+    total = [l for l in sass.splitlines() if l.startswith("| **all kernels**")][0].split("|")
+    utchmma, ldtm, utmaldg, hmma = int(total[3]), int(total[5]), int(total[6]), int(total[8])
+    assert utchmma > 500 and ldtm > 100 and utmaldg > 500 and hmma > 300
+    assert "encoder_stack_kernel" in sass and "segnet_head_kernel" in sass and "poolfeat_partial_mma_kernel" in sass
+
+
+def test_integration_doc_maps_every_exported_symbol():
+    from disentangledcolorization_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert [s for s in _lib.EXPORTS if s not in text] == []
