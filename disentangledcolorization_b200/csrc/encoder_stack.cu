@@ -16,11 +16,18 @@
 // Precision.  The token path feeds discrete decisions (k-means anchors, arg-max labels), so it keeps fp32-grade accuracy on
 // bf16 tensor cores: every operand is split x = hi + lo (two bf16) and each product is hi*hi + lo*hi + hi*lo with fp32
 // accumulation -- relative error ~2^-16 per product instead of 2^-9.  Softmax statistics, LayerNorm and residuals are fp32.
+// The one product whose left operand is bounded -- P V, with the probabilities relative to a running reference in
+// (0, 2^10] -- runs on the f16 tensor path instead: P as a single fp16 (11 significant bits) against V split into fp16
+// hi + lo, two MMAs per k-step and one conversion per pair instead of three MMAs and a six-instruction split.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <cstring>
 
 namespace {
 
+#ifndef ES_PV_F16
+#define ES_PV_F16 1          // 1: P V on the f16 path (P single fp16, V fp16 hi + lo); 0: bf16 path, P and V both split (3 MMAs)
+#endif
 constexpr int ES_THREADS = 256;
 constexpr int ES_D = 4;                    // ring slots
 constexpr int ES_ROWB = 144;               // shared-memory row pitch: 64 bf16 + 8 padding -> conflict-free ldmatrix
@@ -65,6 +72,22 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// same shape, fp16 operands
+__device__ __forceinline__ void mma16816h(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x0, float x1) {      // fp16 pair, element 0 in the low half-word
+  __half2 h = __floats2half2_rn(x0, x1);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {   // x ~= hi + lo, both fp16
+  __half2 h = __floats2half2_rn(x0, x1);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  lo = pack_h2(x0 - hf.x, x1 - hf.y);
 }
 __device__ __forceinline__ float es_ex2(float x) {
   float y;
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
         make_frags(xp, phi, plo);
       }
       float acc[8][4];
-      auto store_kv = [&](int arr_hi, const float* bias) {
+      auto store_kv = [&](int arr_hi, const float* bias, bool as_f16) {
         uint16_t* d0 = kvb + ((size_t)arr_hi * P.srows + row0) * 64 + 2 * t;
         uint16_t* d1 = kvb + ((size_t)arr_hi * P.srows + row1) * 64 + 2 * t;
         const size_t lo_off = (size_t)P.srows * 64;
@@ -254,10 +277,10 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2*>(bias + 8 * j + 2 * t);
           uint32_t h, lw;
-          split2(acc[j][0] + bb.x, acc[j][1] + bb.y, h, lw);
+          if (as_f16) split2h(acc[j][0] + bb.x, acc[j][1] + bb.y, h, lw); else split2(acc[j][0] + bb.x, acc[j][1] + bb.y, h, lw);
           *reinterpret_cast<uint32_t*>(d0 + 8 * j) = h;
           *reinterpret_cast<uint32_t*>(d0 + lo_off + 8 * j) = lw;
-          split2(acc[j][2] + bb.x, acc[j][3] + bb.y, h, lw);
+          if (as_f16) split2h(acc[j][2] + bb.x, acc[j][3] + bb.y, h, lw); else split2(acc[j][2] + bb.x, acc[j][3] + bb.y, h, lw);
           *reinterpret_cast<uint32_t*>(d1 + 8 * j) = h;
           *reinterpret_cast<uint32_t*>(d1 + lo_off + 8 * j) = lw;
         }
@@ -265,14 +288,14 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
       uint32_t slot = advance(it + 0);
       zero_tile(acc);
       gemm_chunk(acc, phi, plo, slot, lane);
-      store_kv(0, svl + 64);
+      store_kv(0, svl + 64, false);      // keys: bf16 hi | lo
       {
         uint32_t xhi[4][4], xlo[4][4];
         make_frags(x, xhi, xlo);
         slot = advance(it + 1);
         zero_tile(acc);
         gemm_chunk(acc, xhi, xlo, slot, lane);
-        store_kv(2, svl + 128);
+        store_kv(2, svl + 128, ES_PV_F16 != 0);     // values: fp16 hi | lo (the P V product runs on the f16 path)
       }
       es_cluster_arrive();                       // this CTA's keys/values of layer l are written
       slot = advance(it + 2);
@@ -289,11 +312,15 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
     kv_ready = l;
     try_issue();
 
-    // ---- attention over all keys of the image, 32 per ring item; scores are in log2 units (scale folded into Wq')
+    // ---- attention over all keys of the image, 32 per ring item; scores are in log2 units (scale folded into Wq').
+    // Softmax against a LAZY reference: exp2(s - m) / sum exp2(s - m) is the same for any m, so the reference of a row is
+    // re-centred (cross-lane max, rescale of O and the row sum) only for the first block and when a score exceeds it by
+    // more than 2^10 -- one warp vote per (head, block) instead of a shuffle / max / exp2 / rescale chain.  The reference
+    // enters through the accumulator's initial value (-m), so the MMA delivers s - m directly.
     float o[8][4], mrow[8][2], lsum[8][2];
     zero_tile(o);
 #pragma unroll
-    for (int h = 0; h < 8; ++h) { mrow[h][0] = mrow[h][1] = -INFINITY; lsum[h][0] = lsum[h][1] = 0.f; }
+    for (int h = 0; h < 8; ++h) { mrow[h][0] = mrow[h][1] = 0.f; lsum[h][0] = lsum[h][1] = 0.f; }
     for (int kb = 0; kb < n_kv; ++kb) {
       const uint32_t slot = advance(it + 3 + kb);
       const uint32_t la = slot + (uint32_t)lane * ES_ROWB;
@@ -310,7 +337,8 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
         float s[4][4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-          s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+          s[n][0] = s[n][1] = -mrow[h][0];
+          s[n][2] = s[n][3] = -mrow[h][1];
           mma16816(s[n], qa, kh[n], kh[n]);
           mma16816(s[n], qa, kl[n], kl[n]);
         }
@@ -326,25 +354,38 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
         float mx1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
         mx0 = fmaxf(mx0, fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
         mx1 = fmaxf(mx1, fmaxf(fmaxf(s[2][2], s[2][3]), fmaxf(s[3][2], s[3][3])));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(mrow[h][0], mx0), mn1 = fmaxf(mrow[h][1], mx1);   // finite: every block holds a valid key
-        const float c0 = es_ex2(mrow[h][0] - mn0), c1 = es_ex2(mrow[h][1] - mn1);
-        mrow[h][0] = mn0; mrow[h][1] = mn1;
+        if (kb == 0 || __any_sync(0xffffffffu, fmaxf(mx0, mx1) > 10.0f)) {
+          // re-centre: row maxima over the quad; block 0 always (the initial reference 0 may be far off either way),
+          // later blocks only upwards
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          const float d0 = (kb == 0 || mx0 > 0.f) ? mx0 : 0.f, d1 = (kb == 0 || mx1 > 0.f) ? mx1 : 0.f;   // finite: a valid key exists
+          const float c0 = kb == 0 ? 1.f : es_ex2(-d0), c1 = kb == 0 ? 1.f : es_ex2(-d1);   // block 0: O and the sums are still zero
+          mrow[h][0] += d0; mrow[h][1] += d1;
+          lsum[h][0] *= c0; lsum[h][1] *= c1;
+          o[h][0] *= c0; o[h][1] *= c0; o[h][2] *= c1; o[h][3] *= c1;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) { s[n][0] -= d0; s[n][1] -= d0; s[n][2] -= d1; s[n][3] -= d1; }
+        }
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-          s[n][0] = es_ex2(s[n][0] - mn0); s[n][1] = es_ex2(s[n][1] - mn0);
-          s[n][2] = es_ex2(s[n][2] - mn1); s[n][3] = es_ex2(s[n][3] - mn1);
+          s[n][0] = es_ex2(s[n][0]); s[n][1] = es_ex2(s[n][1]);
+          s[n][2] = es_ex2(s[n][2]); s[n][3] = es_ex2(s[n][3]);
           rs0 += s[n][0] + s[n][1]; rs1 += s[n][2] + s[n][3];
         }
-        lsum[h][0] = fmaf(lsum[h][0], c0, rs0); lsum[h][1] = fmaf(lsum[h][1], c1, rs1);   // per-thread partial row sums
-        o[h][0] *= c0; o[h][1] *= c0; o[h][2] *= c1; o[h][3] *= c1;
+        lsum[h][0] += rs0; lsum[h][1] += rs1;      // per-thread partial row sums
         uint32_t vh[4], vl[4];
         ldsm_x4_t(vh, la + 64 * ES_ROWB + h * 16);
         ldsm_x4_t(vl, la + 96 * ES_ROWB + h * 16);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {            // keys 16u..16u+15 of the block = score tiles 2u, 2u+1
+#if ES_PV_F16
+          const uint32_t pf[4] = {pack_h2(s[2 * u][0], s[2 * u][1]), pack_h2(s[2 * u][2], s[2 * u][3]),
+                                  pack_h2(s[2 * u + 1][0], s[2 * u + 1][1]), pack_h2(s[2 * u + 1][2], s[2 * u + 1][3])};
+          mma16816h(o[h], pf, vh[2 * u], vh[2 * u + 1]);
+          mma16816h(o[h], pf, vl[2 * u], vl[2 * u + 1]);
+#else
           uint32_t ph[4], pl[4];
           split2(s[2 * u][0], s[2 * u][1], ph[0], pl[0]);
           split2(s[2 * u][2], s[2 * u][3], ph[1], pl[1]);
@@ -353,6 +394,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) encoder_stack_kernel(const EsPa
           mma16816(o[h], ph, vh[2 * u], vh[2 * u + 1]);
           mma16816(o[h], pl, vh[2 * u], vh[2 * u + 1]);
           mma16816(o[h], ph, vl[2 * u], vl[2 * u + 1]);
+#endif
         }
       }
     }

@@ -266,7 +266,7 @@ def test_encoder_stack_fused_matches_oracle(synth_sd, B, H, W):
         assert eng.handle.launches() - before == 1
         err = (out.cpu().view(B, S, 64) - ref).abs().max()
         print(f"fused {stack} B={B} S={S}: max err {float(err):.2e}")
-        assert err < 1e-4, float(err)
+        assert err < 5e-4, float(err)          # P V on the f16 path: P carries 11 significant bits (exact variant: -DES_PV_F16=0, 5e-5)
         # a second run into the ping-pong scratch gives the same bits (no stale key/value reads)
         out2 = torch.empty_like(out)
         eng._encoder_stack(stack, x.cuda().view(B * S, 64).contiguous(), out2, ws, B, _stream())
