@@ -54,6 +54,16 @@ def test_round2_evidence_is_committed_and_consistent():
     conv_flops = sum(v["flops"] for v in d["per_op"].values())
     assert abs(conv_flops / 64 / 1e9 - 254.93) < 0.5
     assert "segnet.net.conv0a+conv0b+conv1a" in d["per_op"]
+    # the ncu launch list of the same bench command holds exactly two timed steps of launches
+    from disentangledcolorization_b200.tools import ncu_summary
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "s.md")
+        ncu_summary.launches(os.path.join(ROOT, "profiles", "r2_launches_bench.csv"), out, "test")
+        text = open(out).read()
+    total = [l for l in text.splitlines() if l.startswith("| **total**")][0]
+    assert int(total.split("|")[2]) == 2 * line["gpu_launches"] // line["steps"]
+    assert "encoder_stack_kernel" in text and "segnet_head_kernel" in text and "attention_kernel" not in text
     sass = open(os.path.join(ROOT, "profiles", "sass_opcodes.md")).read()
     total = [l for l in sass.splitlines() if l.startswith("| **all kernels**")][0].split("|")
     utchmma, ldtm, utmaldg, hmma = int(total[3]), int(total[5]), int(total[6]), int(total[8])
