@@ -20,7 +20,7 @@ EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create"
            "disco_conv_tc_supported", "disco_conv_tc_weight_elems", "disco_conv_tc_pack_weights",
            "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows",
            "disco_encoder_stack", "disco_encoder_stack_pack", "disco_encoder_stack_scratch_elems", "disco_segnet_head", "disco_lab2rgb_u8", "disco_ce_rebalance",
-           "disco_spixel_recon_loss", "disco_encode_ab2ind"]
+           "disco_spixel_recon_loss", "disco_encode_ab2ind", "disco_host_png_bound", "disco_host_png_encode", "disco_host_png_write"]
 
 
 class ConvSrc(C.Structure):
@@ -94,6 +94,10 @@ def load():
     lib.disco_ce_rebalance.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_void_p] * 4
     lib.disco_spixel_recon_loss.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.disco_host_choice_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int32)] + [C.c_int] * 5 + [C.c_void_p]
+    lib.disco_host_png_bound.argtypes = [C.c_int, C.c_int]
+    lib.disco_host_png_bound.restype = C.c_longlong
+    lib.disco_host_png_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]
+    lib.disco_host_png_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong]
     lib.disco_poolfeat.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.disco_upfeat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
     lib.disco_linear.argtypes = [C.c_void_p, C.POINTER(LinearDesc), C.c_void_p]
@@ -154,3 +158,31 @@ def choice_rows(n_tokens, n_clusters, rows, keep=None):
                                         int(lo), int(hi), C.c_void_p(out.ctypes.data)), "disco_host_choice_rows")
     np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
     return out
+
+
+def _rgb_u8(rgb):
+    import numpy as np
+    if rgb.dtype != np.uint8 or rgb.ndim != 3 or rgb.shape[2] != 3 or rgb.strides[2] != 1 or rgb.strides[1] != 3:
+        raise ValueError("expected an (H, W, 3) uint8 array with contiguous rows")
+    return rgb
+
+
+def png_encode(rgb):
+    """(H, W, 3) uint8 RGB -> the bytes of a PNG file (disco_host_png_encode; host only, the GIL is released)."""
+    import numpy as np
+    rgb = _rgb_u8(rgb)
+    lib = load()
+    H, W = int(rgb.shape[0]), int(rgb.shape[1])
+    cap = int(lib.disco_host_png_bound(H, W))
+    buf = np.empty(cap, np.uint8)
+    n = C.c_longlong(0)
+    check(lib.disco_host_png_encode(C.c_void_p(rgb.ctypes.data), H, W, int(rgb.strides[0]), C.c_void_p(buf.ctypes.data), cap, C.byref(n)),
+          "disco_host_png_encode")
+    return buf[:n.value].tobytes()
+
+
+def png_write(path, rgb):
+    """Encode and write one PNG file (disco_host_png_write), replacing Image.fromarray(rgb).save(path) of utils/util.py:106."""
+    rgb = _rgb_u8(rgb)
+    check(load().disco_host_png_write(os.fsencode(path), C.c_void_p(rgb.ctypes.data), int(rgb.shape[0]), int(rgb.shape[1]),
+                                      int(rgb.strides[0])), "disco_host_png_write")

@@ -292,6 +292,19 @@ int disco_lab2rgb_u8(disco_handle* h, const float* gray, const float* ab, int ba
 int disco_host_choice_rows(uint32_t* mt_key, int32_t* mt_pos, int S, int K, int rows, int keep_lo, int keep_hi,
                            int32_t* out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host helper (no device work): PNG encoder for the CLI's writer threads, replacing the reference's
+ * `Image.fromarray(rgb).save(path, "PNG")` (utils/util.py:91-106 through main/colorizer/inference.py:131-135).
+ * 8-bit RGB, H x W x 3 with `row_stride` bytes between rows.  Same decoded pixels as any PNG writer; the file bytes differ
+ * (Sub filter on every row, one dynamic-Huffman deflate block of literals + distance-1 runs, no LZ77 search): ~0.5 ms per
+ * 256 x 256 image against 7.7 ms (OpenCV/libpng level 1) and 18-26 ms (PIL level 6) on one host core.
+ * disco_host_png_bound: capacity `out` must have.  disco_host_png_encode: file image into out[0 .. *out_len).
+ * disco_host_png_write: encode + write to `path`. */
+long long disco_host_png_bound(int H, int W);
+int disco_host_png_encode(const uint8_t* rgb, int H, int W, long long row_stride, uint8_t* out, long long cap,
+                          long long* out_len);
+int disco_host_png_write(const char* path, const uint8_t* rgb, int H, int W, long long row_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,3 +66,51 @@ def test_fast_reader_is_bit_identical_to_fetch_data(tmp_path):
         hw2 = inference._fetch_into(path, g, a)
         assert hw2 == hw
         assert np.array_equal(g, gray[0].numpy()) and np.array_equal(a, ab[0].numpy())
+
+
+def _png_cases():
+    import cv2
+    rng = np.random.default_rng(5)
+    small = rng.random((18, 18, 3)).astype(np.float32)
+    smooth = np.clip(cv2.resize(small, (256, 256), interpolation=cv2.INTER_CUBIC) * 255, 0, 255).astype(np.uint8)
+    noisy = np.clip(smooth + rng.normal(0, 3, smooth.shape), 0, 255).astype(np.uint8)
+    skew = np.cumsum(np.minimum(rng.geometric(0.5, (120, 200, 3)), 255), axis=1, dtype=np.uint64).astype(np.uint8)
+    big = rng.integers(0, 256, (64, 80, 3), dtype=np.uint8)
+    return {"smooth": smooth, "noisy": noisy, "flat": np.full((64, 48, 3), 7, np.uint8), "zeros": np.zeros((5, 3, 3), np.uint8),
+            "1x1": np.array([[[1, 2, 3]]], np.uint8), "random": rng.integers(0, 256, (100, 77, 3), dtype=np.uint8),
+            "deep_tree": skew, "row_stride_view": big[:50, :60], "long_runs": np.repeat(big[:8, :3], 100, axis=1)}
+
+
+def test_native_png_writer_stores_the_pixels_pil_would(tmp_path):
+    """disco_host_png_write replaces Image.fromarray(rgb).save(path, 'PNG') (reference utils/util.py:106): PIL and OpenCV
+    decode the file to exactly the array that was written, and the stream passes PIL's CRC / Adler verification."""
+    import cv2
+    from PIL import Image
+    from disentangledcolorization_b200 import _lib
+    for name, img in _png_cases().items():
+        path = str(tmp_path / f"{name}.png")
+        _lib.png_write(path, img)
+        Image.open(path).verify()
+        with Image.open(path) as im:
+            assert im.mode == "RGB" and im.size == (img.shape[1], img.shape[0]), name
+            assert np.array_equal(np.asarray(im), img), name
+        assert np.array_equal(cv2.cvtColor(cv2.imread(path, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB), img), name
+        with open(path, "rb") as f:
+            assert f.read() == _lib.png_encode(img), name
+        ref = str(tmp_path / "ref.png")
+        Image.fromarray(np.ascontiguousarray(img)).save(ref, "PNG")
+        if img.size > 10000:                                  # not LZ77: larger than PIL's level 6, but never by much
+            assert os.path.getsize(path) < 1.6 * os.path.getsize(ref) + 2048, (name, os.path.getsize(path), os.path.getsize(ref))
+
+
+def test_native_png_writer_rejects_bad_input(tmp_path):
+    import pytest
+    from disentangledcolorization_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.png_encode(np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(ValueError):
+        _lib.png_encode(np.zeros((4, 4, 4), np.uint8))
+    with pytest.raises(ValueError):
+        _lib.png_encode(np.zeros((4, 8, 3), np.uint8)[:, ::2])
+    with pytest.raises(RuntimeError):
+        _lib.png_write(str(tmp_path / "no_such_dir" / "a.png"), np.zeros((4, 4, 3), np.uint8))
