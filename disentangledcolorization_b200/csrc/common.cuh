@@ -87,4 +87,9 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 int conv_simt_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 bool conv_tc_supported(const disco_conv_desc* d);
+// narrow-layer mma.sync kernels (conv_narrow.cu): claim a bf16 descriptor before the tcgen05 plan is consulted
+bool conv_narrow_match(const disco_conv_desc* d);
+int64_t conv_narrow_weight_elems(const disco_conv_desc* d);
+int conv_narrow_pack(const disco_conv_desc* d, const float* w32_host, uint16_t* out_host);
+int conv_narrow_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 void conv_tc_cache_clear(disco_handle* h);   // frees the cached plans of h->device (caller holds the device guard)

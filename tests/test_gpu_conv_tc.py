@@ -234,3 +234,60 @@ def test_cin1_layers_stay_on_cuda_cores():
     w, b = torch.randn(64, 1, 3, 3, generator=g) / 3, torch.randn(64, generator=g) * 0.1
     out = _run_tc(_lib.CONV3, 1, [(gray, 0, True)], [w], b, 64, 32, 32, act=_lib.ACT_LRELU, slope=0.2, expect_tc=False)
     _check(out, F.leaky_relu(F.conv2d(gray, w, b, padding=1), 0.2))
+
+
+# ---- narrow-layer mma.sync kernels (csrc/conv_narrow.cu): SpixelNet's decoder tail (deconv0, conv0_1, pred_mask0 + softmax);
+# the 32-channel shapes below stay on the tcgen05 resident kernel and are kept as ragged-size cases for it
+NARROW_SIZES = [(2, 32, 32), (1, 48, 80), (3, 20, 36), (1, 16, 100)]
+
+
+@pytest.mark.parametrize("B,H,W", NARROW_SIZES, ids=str)
+def test_narrow_conv0_1_two_16_channel_sources(B, H, W):
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + H + W)
+    a, s = _bf(torch.randn(B, 16, H, W, generator=g)), _bf(torch.randn(B, 16, H, W, generator=g))
+    w = _bf(torch.randn(16, 32, 3, 3, generator=g) / (32 * 9) ** 0.5)
+    b = torch.randn(16, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(torch.cat((a, s), 1), w, b, padding=1), 0.1)
+    out = _run_tc(_lib.CONV3, 1, [(a, 0, False), (s, 0, False)], [w[:, :16], w[:, 16:]], b, 16, H, W, act=_lib.ACT_LRELU, slope=0.1)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W", NARROW_SIZES, ids=str)
+def test_narrow_pred_mask_softmax9(B, H, W):
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + H + W + 1)
+    x = _bf(torch.randn(B, 16, H, W, generator=g))
+    w9, b9 = _bf(torch.randn(9, 16, 3, 3, generator=g) * 0.2), torch.randn(9, generator=g)
+    out = _run_tc(_lib.CONV3, 1, [(x, 0, False)], [w9], b9, 9, H, W, head=_lib.HEAD_SOFTMAX9)
+    ref = torch.softmax(F.conv2d(x, w9, b9, padding=1), 1)
+    assert (out - ref).abs().max() < 1e-5                  # bf16 operands are exact products: only fp32 summation order differs
+    assert (out.sum(1) - 1).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W", NARROW_SIZES, ids=str)
+@pytest.mark.parametrize("two", [False, True], ids=["conv1b", "conv1_1"])
+def test_narrow_32_channel_layers(B, H, W, two):
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + H + W + 2 + int(two))
+    cin = 64 if two else 32
+    x = _bf(torch.randn(B, cin, H, W, generator=g))
+    w = _bf(torch.randn(32, cin, 3, 3, generator=g) / (cin * 9) ** 0.5)
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x, w, b, padding=1))
+    srcs = [(x[:, :32], 0, False), (x[:, 32:], 0, False)] if two else [(x, 0, False)]
+    ws = [w[:, :32], w[:, 32:]] if two else [w]
+    out = _run_tc(_lib.CONV3, 1, srcs, ws, b, 32, H, W, act=_lib.ACT_RELU)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 12, 20), (1, 9, 7), (3, 8, 50)], ids=str)
+def test_narrow_deconv0(B, H, W):
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + H + W + 3)
+    x = _bf(torch.randn(B, 32, H, W, generator=g))
+    w = _bf(torch.randn(32, 16, 4, 4, generator=g) / (32 * 4) ** 0.5)
+    b = torch.randn(16, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv_transpose2d(x, w, b, stride=2, padding=1), 0.1)
+    out = _run_tc(_lib.DECONV4, 1, [(x, 0, False)], [w], b, 16, 2 * H, 2 * W, act=_lib.ACT_LRELU, slope=0.1)
+    _check(out, ref)
