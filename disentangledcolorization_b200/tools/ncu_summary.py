@@ -30,7 +30,7 @@ def launches(path, out, command):
         a[1] += float(r[iv].replace(",", "")) / 1e6
     total = sum(v[1] for v in agg.values())
     n = sum(v[0] for v in agg.values())
-    conv = sum(v[1] for k, v in agg.items() if k.startswith("conv_"))
+    conv = sum(v[1] for k, v in agg.items() if k.startswith(("conv_", "narrow_", "segnet_head")))
     with open(out, "w") as f:
         f.write(f"# ncu launch list of `{command}`\n\n")
         f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
@@ -38,7 +38,7 @@ def launches(path, out, command):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {v[0]} | {v[1]:.3f} | {100 * v[1] / total:.1f} % |\n")
         f.write(f"| **total** | {n} | {total:.3f} | |\n\n")
-        f.write(f"Convolution kernels (tcgen05 + CUDA-core first layers): {100 * conv / total:.1f} % of the captured device time.\n")
+        f.write(f"Convolution kernels (tcgen05, mma.sync narrow layers, fused SpixelNet head, Cin = 1 layers): {100 * conv / total:.1f} % of the captured device time.\n")
     print(open(out).read())
 
 
