@@ -131,3 +131,21 @@ class ColorLabel:
                                                  _p(self.q_to_ab.to(batch_ab.device)), B, h * w, _p(labels), None,
                                                  stream), "disco_token_labels")
         return labels.view(B, 1, h, w).long()
+
+
+def lab2rgb(lab_rs, l_mean=50, l_norm=50, ab_norm=110):
+    """reference models/basic.py:468-475 (-> lab2xyz -> xyz2rgb, :422-466): normalised Lab (N,3,H,W) in [-1,1] -> RGB in
+    [0,1], fp32 NCHW, one kernel (disco_lab2rgb_norm).  Only the default normalisation constants are built."""
+    if (l_mean, l_norm, ab_norm) != (50, 50, 110):
+        raise _lib.DiscoError("lab2rgb: only l_mean=50, l_norm=50, ab_norm=110 are built")
+    if lab_rs.dim() != 4 or lab_rs.shape[1] != 3:
+        raise _lib.DiscoError(f"lab2rgb: input must be (N,3,H,W), got {tuple(lab_rs.shape)}")
+    handle, stream = _ctx(lab_rs)
+    with torch.cuda.device(lab_rs.device):
+        lab = lab_rs.detach().float()
+        gray, ab = lab[:, 0:1].contiguous(), lab[:, 1:3].contiguous()
+        N, _, H, W = lab.shape
+        out = torch.empty(N, 3, H, W, dtype=torch.float32, device=lab.device)
+        _lib.check(handle.lib.disco_lab2rgb_norm(handle.h, _p(gray), _p(ab), N, H, W, _p(out), None, _lib.F32, 3, None, None, stream),
+                   "disco_lab2rgb_norm")
+    return out

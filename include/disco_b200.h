@@ -293,6 +293,24 @@ int disco_host_choice_rows(uint32_t* mt_key, int32_t* mt_pos, int S, int K, int 
                            int32_t* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Perceptual-loss side ops (config 5; AnchorColorProbLoss._perceptual_loss, models/loss.py:45-49 and VGG19Loss,
+ * models/loss.py:138-223).  The VGG19 convolutions themselves are disco_conv calls (3x3, bias, ReLU).
+ *   disco_lab2rgb_norm: basic.lab2rgb (models/basic.py:431-475; normalised Lab = gray (L-50)/50 and ab/110, fp32 NCHW)
+ *     -> RGB in [0,1] as fp32 NCHW (`rgb_nchw`, may be NULL) and/or VGG19Loss.normalize((rgb-mean)/std) as NHWC
+ *     activations of `dtype` with `cpad` >= 3 channels, channels 3.. zero (`norm_nhwc`, may be NULL; mean3/std3 are HOST arrays).
+ *   disco_rgb_norm: the normalisation / packing alone, for VGG19Loss.forward(x, y) on RGB images (B,3,H,W).
+ *   disco_maxpool2: nn.MaxPool2d(2, 2) on NHWC activations (C % 8 == 0 for bf16, % 4 for fp32; H, W even).
+ *   disco_l1_mean: nn.L1Loss(): out[0] = (accumulate ? out[0] : 0) + weight * mean|x - y| over n elements; `partial` is
+ *     scratch of n_partial floats (the reduction order is fixed by n_partial: deterministic). */
+int disco_lab2rgb_norm(disco_handle* h, const float* gray, const float* ab, int batch, int H, int W, float* rgb_nchw,
+                       void* norm_nhwc, int dtype, int cpad, const float* mean3, const float* std3, void* stream);
+int disco_rgb_norm(disco_handle* h, const float* rgb, int batch, int H, int W, void* norm_nhwc, int dtype, int cpad,
+                   const float* mean3, const float* std3, void* stream);
+int disco_maxpool2(disco_handle* h, int dtype, const void* x, int batch, int H, int W, int C, void* y, void* stream);
+int disco_l1_mean(disco_handle* h, int dtype, const void* x, const void* y, long long n, float weight, int accumulate,
+                  float* partial, int n_partial, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host helper (no device work): PNG encoder for the CLI's writer threads, replacing the reference's
  * `Image.fromarray(rgb).save(path, "PNG")` (utils/util.py:91-106 through main/colorizer/inference.py:131-135).
  * 8-bit RGB, H x W x 3 with `row_stride` bytes between rows.  Same decoded pixels as any PNG writer; the file bytes differ

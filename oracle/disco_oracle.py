@@ -426,3 +426,60 @@ def spixel_loss(prob, feat, k=16):
     f = torch.norm(d[:, :-2], p=2, dim=1).mean()
     p_ = torch.norm(d[:, -2:], p=2, dim=1).mean() / k
     return {"totalLoss": 10 * f + 0.003 * p_, "featLoss": f, "posLoss": p_}
+
+
+# ---- perceptual term of AnchorColorProbLoss (config 5): models/basic.py:422-475, models/loss.py:45-49,138-223 ----------
+def lab2rgb(lab_rs):
+    """basic.lab2rgb: normalised Lab (N,3,H,W) -> RGB [0,1] (lab2xyz, models/basic.py:439-454; xyz2rgb, :409-422)."""
+    L = lab_rs[:, 0] * 50.0 + 50.0
+    a, b = lab_rs[:, 1] * 110.0, lab_rs[:, 2] * 110.0
+    y = (L + 16.0) / 116.0
+    x = a / 500.0 + y
+    z = torch.clamp(y - b / 200.0, min=0.0)
+    out = torch.stack((x, y, z), dim=1)
+    mask = (out > 0.2068966).float()
+    out = (out ** 3.0) * mask + (out - 16.0 / 116.0) / 7.787 * (1 - mask)
+    out = out * torch.tensor((0.95047, 1.0, 1.08883), dtype=out.dtype, device=out.device)[None, :, None, None]
+    r = 3.24048134 * out[:, 0] - 1.53715152 * out[:, 1] - 0.49853633 * out[:, 2]
+    g = -0.96925495 * out[:, 0] + 1.87599 * out[:, 1] + 0.04155593 * out[:, 2]
+    bl = 0.05564664 * out[:, 0] - 0.20404134 * out[:, 1] + 1.05731107 * out[:, 2]
+    rgb = torch.clamp(torch.stack((r, g, bl), dim=1), min=0.0)
+    mask = (rgb > 0.0031308).float()
+    return (1.055 * (rgb ** (1.0 / 2.4)) - 0.055) * mask + 12.92 * rgb * (1 - mask)
+
+
+VGG19_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+VGG_SLICES = {"liu": [2, 7, 12, 21, 30], "lei": [4, 9, 14, 23, 32]}                    # models/loss.py:160-172: slice ends
+VGG_WEIGHTS = {"liu": [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0], "lei": [1.0 / 2.6, 1.0 / 4.8, 1.0 / 3.7, 1.0 / 5.6, 10.0 / 1.5]}
+
+
+def vgg19_loss(convs, x, y, feat_type="liu"):
+    """VGG19Loss.forward (models/loss.py:205-223).  convs: [(weight, bias)] of torchvision vgg19.features in order;
+    x ground truth, y prediction, RGB (N,3,H,W) in [0,1]."""
+    mean = torch.tensor([0.485, 0.456, 0.406], dtype=x.dtype, device=x.device)[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225], dtype=x.dtype, device=x.device)[None, :, None, None]
+    z = torch.cat(((x - mean) / std, (y - mean) / std), 0)
+    N = x.shape[0]
+    ends = VGG_SLICES.get(feat_type, [28])
+    wts = VGG_WEIGHTS.get(feat_type, [1.0])
+    loss, idx, ci, k = 0.0, 0, 0, 0
+    for v in VGG19_CFG:
+        if v == "M":
+            z = F.max_pool2d(z, 2, 2)
+            idx += 1
+        else:
+            w, b = convs[ci]
+            ci += 1
+            z = F.relu(F.conv2d(z, w, b, padding=1))
+            idx += 2
+        if k < len(ends) and idx == ends[k]:
+            loss = loss + wts[k] * (z[:N] - z[N:]).abs().mean()
+            k += 1
+            if k == len(ends):
+                break
+    return loss
+
+
+def perceptual_loss(convs, gray, colors_x, colors_y, feat_type="liu"):
+    """AnchorColorProbLoss._perceptual_loss (models/loss.py:45-49)."""
+    return vgg19_loss(convs, lab2rgb(torch.cat([gray, colors_x], 1)), lab2rgb(torch.cat([gray, colors_y], 1)), feat_type)

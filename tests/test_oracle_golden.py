@@ -91,3 +91,30 @@ def test_oracle_losses_match_reference_fixture():
     assert np.abs(pal.grad.numpy() - g["pal_grad"]).max() < 1e-6 and np.abs(ref.grad.numpy() - g["ref_grad"]).max() < 1e-6
     sp = O.spixel_loss(torch.from_numpy(g["prob"]), torch.from_numpy(g["feat"]), 16)
     assert abs(sp["totalLoss"].item() - float(g["sp_total"])) < 1e-4 and abs(sp["posLoss"].item() - float(g["sp_pos"])) < 1e-6
+
+
+def _seeded_vgg_convs():
+    """[(weight, bias)] of torchvision's random-init vgg19 under the fixture's seed (oracle/make_golden_vgg.py)."""
+    import make_golden_vgg
+    vgg = make_golden_vgg.seeded_vgg19()
+    convs = [(m.weight.detach(), m.bias.detach()) for m in vgg.features if isinstance(m, torch.nn.Conv2d)]
+    return vgg, convs
+
+
+def test_oracle_perceptual_term_matches_reference_fixture():
+    """lab2rgb and VGG19Loss ('liu', 'lei', conv4_4 variants) of the oracle == the unmodified reference's values
+    (tests/golden/vgg_loss.npz, oracle/make_golden_vgg.py), with the VGG weights rebuilt from the fixture's seed."""
+    import disco_oracle as O
+    g = load_golden("vgg_loss")
+    vgg, convs = _seeded_vgg_convs()
+    checksum = float(sum(p.detach().double().abs().sum() for p in vgg.features.parameters()))
+    assert abs(checksum - float(g["weight_checksum"])) < 1e-6 * checksum, "torchvision's seeded init no longer reproduces the fixture's weights"
+    gray, ab_x, ab_y = (torch.from_numpy(g[k]) for k in ("gray", "ab_x", "ab_y"))
+    rgb_x = O.lab2rgb(torch.cat([gray, ab_x], 1))
+    assert np.abs(rgb_x.numpy() - g["rgb_x"]).max() < 1e-6
+    rgb_y = O.lab2rgb(torch.cat([gray, ab_y], 1))
+    with torch.no_grad():
+        for ft in ("liu", "lei", "conv4_4"):
+            v = float(O.vgg19_loss(convs, rgb_x, rgb_y, ft))
+            assert abs(v - float(g["loss_" + ft])) < 1e-5 * abs(float(g["loss_" + ft])) + 1e-7, (ft, v, float(g["loss_" + ft]))
+        assert abs(float(O.perceptual_loss(convs, gray, ab_x, ab_y)) - float(g["perceptual"])) < 1e-6
