@@ -126,7 +126,84 @@ __global__ void l1_final_kernel(const float* __restrict__ partial, int nb, doubl
   }
 }
 
+// AnchorColorProbLoss._laplace_gradient (models/loss.py:51-57): depthwise 3x3 Laplacian [[1,1,1],[1,-8,1],[1,1,1]] without
+// padding of prediction and target, L1 mean of the difference.  The Laplacian is linear, so one pass over d = target - pred.
+__device__ __forceinline__ float lap_at(const float* __restrict__ t, const float* __restrict__ p, int W, size_t c) {
+  float s = 0.f;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const size_t i = c + (ptrdiff_t)dy * W + dx;
+      s += (dy == 0 && dx == 0 ? -8.0f : 1.0f) * (t[i] - p[i]);
+    }
+  return s;
+}
+
+__global__ void laplace_l1_kernel(const float* __restrict__ pred, const float* __restrict__ target, int planes, int H, int W,
+                                  float* __restrict__ sign_map, float* __restrict__ partial) {
+  __shared__ float red[L1_BLOCK];
+  const int Ho = H - 2, Wo = W - 2;
+  const size_t n = (size_t)planes * Ho * Wo;
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * L1_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * L1_BLOCK) {
+    const int ox = (int)(i % Wo);
+    const size_t r = i / Wo;
+    const int oy = (int)(r % Ho);
+    const size_t pl = r / Ho;
+    const float v = lap_at(target, pred, W, (pl * H + oy + 1) * W + ox + 1);
+    s += fabsf(v);
+    if (sign_map) sign_map[i] = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = L1_BLOCK / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// d loss / d pred[y][x] = -(1/n) * sum over the outputs (oy, ox) whose window holds (y, x) of k[y-oy][x-ox] * sign(oy, ox)
+__global__ void laplace_l1_grad_kernel(const float* __restrict__ sign_map, int planes, int H, int W, float inv_n, float* __restrict__ grad) {
+  const int Ho = H - 2, Wo = W - 2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)planes * H * W) return;
+  const int x = (int)(idx % W);
+  const size_t r = idx / W;
+  const int y = (int)(r % H);
+  const size_t pl = r / H;
+  float s = 0.f;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int oy = y - 1 - dy, ox = x - 1 - dx;          // output whose tap (dy, dx) reads (y, x)
+      if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) s += (dy == 0 && dx == 0 ? -8.0f : 1.0f) * sign_map[(pl * Ho + oy) * Wo + ox];
+    }
+  grad[idx] = -s * inv_n;
+}
+
 }  // namespace
+
+extern "C" int disco_laplace_l1(disco_handle* h, const float* pred, const float* target, int batch, int C, int H, int W,
+                                float* sign_scratch, float* partial, int n_partial, float* out, float* grad_pred, void* stream) {
+  DISCO_CHECK_ARG(h && pred && target && partial && out, "laplace_l1: null pointer");
+  DISCO_CHECK_ARG(batch > 0 && C > 0 && H >= 3 && W >= 3 && n_partial > 0, "laplace_l1: needs H, W >= 3 (got %dx%d)", H, W);
+  DISCO_CHECK_ARG(!grad_pred || sign_scratch, "laplace_l1: the gradient needs the sign scratch buffer");
+  DiscoDeviceGuard guard(h);
+  const long long n = (long long)batch * C * (H - 2) * (W - 2);
+  const long long want = (n + L1_BLOCK - 1) / L1_BLOCK;
+  const int nb = (int)(want < n_partial ? want : n_partial);
+  laplace_l1_kernel<<<nb, L1_BLOCK, 0, (cudaStream_t)stream>>>(pred, target, batch * C, H, W, sign_scratch, partial);
+  DISCO_LAUNCH_CHECK(h);
+  l1_final_kernel<<<1, L1_BLOCK, 0, (cudaStream_t)stream>>>(partial, nb, 1.0 / (double)n, 1.0f, out, 0);
+  DISCO_LAUNCH_CHECK(h);
+  if (grad_pred) {
+    const size_t m = (size_t)batch * C * H * W;
+    laplace_l1_grad_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sign_scratch, batch * C, H, W, (float)(1.0 / (double)n), grad_pred);
+    DISCO_LAUNCH_CHECK(h);
+  }
+  return DISCO_OK;
+}
 
 static int lab2rgb_norm_impl(disco_handle* h, const float* gray, const float* ab, int batch, int H, int W, float* rgb_nchw,
                              void* norm_nhwc, int dtype, int cpad, const float* mean3, const float* std3, void* stream);

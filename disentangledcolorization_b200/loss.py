@@ -6,8 +6,8 @@ Built: `AnchorColorProbLoss` token terms (palLoss, refLoss: cross-entropy with g
 (forward value AND d loss / d logits; `loss.backward()` delivers the re-balanced gradient to `pal_prob` / `ref_prob` when
 they require grad), its perceptual term (`enhanced=True`: `VGG19Loss` = Lab -> RGB, normalisation, the VGG19 feature stack
 through disco_conv, 2x2 max pooling and the five weighted L1 means, all on the device; a VALUE only -- the reference feeds
-it so that no gradient reaches the model), `SPixelLoss` (forward value).  NOT built: `hint2regress`,
-`with_grad` (Laplacian term), and the backward of the conv / transformer kernels; they raise.
+it so that no gradient reaches the model), the Laplacian term (`with_grad=True`: value and d loss / d pred_color),
+`SPixelLoss` (forward value).  NOT built: `hint2regress` (raises) and the backward of the conv / transformer kernels.
 """
 import ctypes as C
 
@@ -55,15 +55,41 @@ class _CERebalance(torch.autograd.Function):
         return (ctx.grad * grad_out if ctx.grad is not None else None), None, None
 
 
+class _LaplaceL1(torch.autograd.Function):
+    """AnchorColorProbLoss._laplace_gradient (loss.py:51-57): value and d loss / d pred from disco_laplace_l1."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        if pred.dim() != 4 or tuple(pred.shape) != tuple(target.shape):
+            raise _lib.DiscoError(f"_laplace_gradient: pred and target must both be (N,C,H,W), got {tuple(pred.shape)} and {tuple(target.shape)}")
+        handle, stream = _ctx(pred)
+        with torch.cuda.device(pred.device):
+            p, t = pred.detach().float().contiguous(), target.detach().float().contiguous()
+            N, Cc, H, W = p.shape
+            need = pred.requires_grad
+            sign = torch.empty(N * Cc * (H - 2) * (W - 2), dtype=torch.float32, device=p.device) if need else None
+            grad = torch.empty_like(p) if need else None
+            partial = torch.empty(1184, dtype=torch.float32, device=p.device)
+            out = torch.empty(1, dtype=torch.float32, device=p.device)
+            _lib.check(handle.lib.disco_laplace_l1(handle.h, _p(p), _p(t), N, Cc, H, W, _p(sign), _p(partial), partial.numel(), _p(out),
+                                                   _p(grad), stream), "disco_laplace_l1")
+        ctx.grad = grad
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (ctx.grad * grad_out if ctx.grad is not None else None), None
+
+
 class AnchorColorProbLoss:
     """reference models/loss.py:33-87."""
 
     def __init__(self, hint2regress=False, enhanced=False, with_grad=False, mpdist=False, gpu_no=0, vgg_loss=None):
         """`vgg_loss` [extension]: a ready `VGG19Loss` (e.g. built from a local torchvision model); by default the
         constructor builds one exactly as the reference does (loss.py:42-43: downloads the pretrained VGG19)."""
-        if hint2regress or with_grad:
-            raise _lib.DiscoError("AnchorColorProbLoss: hint2regress / with_grad (Laplacian term) are not built; the token-level "
-                                  "cross-entropy terms and the perceptual term are (SURVEY 8a a18)")
+        if hint2regress:
+            raise _lib.DiscoError("AnchorColorProbLoss: hint2regress is not built (the reference's own training branch for it is "
+                                  "broken, SURVEY 8b); the cross-entropy, perceptual and Laplacian terms are (SURVEY 8a a18)")
         self.mpdist, self.gpu_no = mpdist, gpu_no
         self.hint2regress, self.enhanced, self.with_grad = hint2regress, enhanced, with_grad
         if self.enhanced:
@@ -74,12 +100,18 @@ class AnchorColorProbLoss:
         normalisation are one kernel per image set (no RGB tensor in HBM)."""
         return self.VGGLoss.from_lab(input_grays, input_colors, pred_colors)
 
+    def _laplace_gradient(self, pred_AB, target_AB):
+        """reference loss.py:51-57."""
+        return _LaplaceL1.apply(pred_AB, target_AB)
+
     def __call__(self, data, epoch_no):
         pal = _CERebalance.apply(data["pal_prob"], data["target_label"], data["class_weight"])       # loss.py:61-70
         ref = _CERebalance.apply(data["ref_prob"], data["target_label"], data["class_weight"])       # loss.py:75-77
         rec = torch.zeros_like(pal)                                                                    # loss.py:78
         if self.enhanced:                                                                              # loss.py:79-81 (argument order as there)
             rec = 5.0 * self._perceptual_loss(data["input_gray"], data["pred_color"], data["input_color"])
+            if self.with_grad:                                                                         # loss.py:82-84
+                rec = rec + self._laplace_gradient(data["pred_color"], data["input_color"])
         return {"totalLoss": pal + ref + rec, "palLoss": pal, "refLoss": ref, "recLoss": rec}
 
 

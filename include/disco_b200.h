@@ -309,6 +309,11 @@ int disco_rgb_norm(disco_handle* h, const float* rgb, int batch, int H, int W, v
 int disco_maxpool2(disco_handle* h, int dtype, const void* x, int batch, int H, int W, int C, void* y, void* stream);
 int disco_l1_mean(disco_handle* h, int dtype, const void* x, const void* y, long long n, float weight, int accumulate,
                   float* partial, int n_partial, float* out, void* stream);
+/* AnchorColorProbLoss._laplace_gradient (models/loss.py:51-57, `with_grad=True`): out[0] = mean |Lap(target) - Lap(pred)| with
+ * the 3x3 Laplacian [[1,1,1],[1,-8,1],[1,1,1]] per channel, no padding; fp32 NCHW.  grad_pred (may be NULL) receives
+ * d out / d pred; sign_scratch holds batch*C*(H-2)*(W-2) floats (required with grad_pred). */
+int disco_laplace_l1(disco_handle* h, const float* pred, const float* target, int batch, int C, int H, int W,
+                     float* sign_scratch, float* partial, int n_partial, float* out, float* grad_pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host helper (no device work): PNG encoder for the CLI's writer threads, replacing the reference's

@@ -483,3 +483,10 @@ def vgg19_loss(convs, x, y, feat_type="liu"):
 def perceptual_loss(convs, gray, colors_x, colors_y, feat_type="liu"):
     """AnchorColorProbLoss._perceptual_loss (models/loss.py:45-49)."""
     return vgg19_loss(convs, lab2rgb(torch.cat([gray, colors_x], 1)), lab2rgb(torch.cat([gray, colors_y], 1)), feat_type)
+
+
+def laplace_gradient(pred_ab, target_ab):
+    """AnchorColorProbLoss._laplace_gradient (models/loss.py:51-57)."""
+    Cc = pred_ab.shape[1]
+    kernel = torch.tensor([[1, 1, 1], [1, -8, 1], [1, 1, 1]], dtype=pred_ab.dtype, device=pred_ab.device).view(1, 1, 3, 3).repeat(Cc, 1, 1, 1)
+    return F.l1_loss(F.conv2d(target_ab, kernel, groups=Cc), F.conv2d(pred_ab, kernel, groups=Cc))

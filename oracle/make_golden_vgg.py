@@ -8,7 +8,8 @@ through oracle/ref_harness.py, CPU).
 The reference downloads torchvision's pretrained VGG19; there is no network here, so `torchvision.models.vgg19` is replaced
 by a wrapper that returns the RANDOM-INIT torchvision model built under torch.manual_seed(VGG_SEED) -- the reference code
 that slices it, normalises the images and forms the weighted L1 sums runs unmodified.  Tests rebuild the same weights from
-the same seed (the fixture stores a checksum of them), so only inputs and results are committed.
+the same seed (the fixture stores a checksum of them), so only inputs and results are committed.  One more CPU shim for
+the Laplacian term: `Tensor.get_device()` is -1 on CPU, which `torch.tensor(..., device=-1)` (loss.py:53) rejects.
 """
 import os
 import sys
@@ -62,6 +63,12 @@ def main():
                 out["loss_" + ft] = float(crit(rgb_x, rgb_y))
             full = ref_loss.AnchorColorProbLoss(hint2regress=False, enhanced=True, with_grad=False, mpdist=False, gpu_no=0)
             out["perceptual"] = float(full._perceptual_loss(gray, ab_x, ab_y))
+        # Laplacian term (with_grad=True): value and the gradient autograd delivers to the prediction
+        torch.Tensor.get_device = lambda self: self.device if self.device.type == "cpu" else self.device.index
+        pred = ab_y.clone().requires_grad_(True)
+        lap = full._laplace_gradient(pred, ab_x)
+        lap.backward()
+        out["laplace"], out["laplace_grad"] = float(lap), pred.grad.numpy()
         vgg = seeded_vgg19()
         out["weight_checksum"] = float(sum(p.double().abs().sum() for p in vgg.features.parameters()))
     finally:

@@ -42,7 +42,7 @@ def test_anchor_color_prob_loss_matches_reference_values_and_gradients():
     assert np.abs(pal.grad.cpu().numpy() - g["pal_grad"]).max() < 1e-6
     assert np.abs(ref.grad.cpu().numpy() - g["ref_grad"]).max() < 1e-6
     with pytest.raises(Exception):
-        loss.AnchorColorProbLoss(with_grad=True)             # Laplacian term: not built
+        loss.AnchorColorProbLoss(hint2regress=True)          # not built (broken in the reference's own training branch)
 
 
 def test_ce_rebalance_large_case_with_ignored_tokens_matches_oracle():
@@ -159,6 +159,28 @@ def test_anchor_color_prob_loss_enhanced_adds_five_times_the_perceptual_term():
     want = 5.0 * float(g["perceptual"])
     assert abs(d["recLoss"].item() - want) < 1e-4 * want
     assert abs(d["totalLoss"].item() - (float(gl["totalLoss"]) + want)) < 1e-4
+
+
+def test_laplacian_term_matches_reference_value_and_gradient():
+    """with_grad=True (loss.py:51-57,82-84): value and d loss / d pred_color == the reference's autograd."""
+    from disentangledcolorization_b200 import loss
+    g, gl = load_golden("vgg_loss"), load_golden("loss_terms")
+    crit = loss.AnchorColorProbLoss(hint2regress=False, enhanced=True, with_grad=True,
+                                    vgg_loss=loss.VGG19Loss(vgg_model=_seeded_vgg(), precision="fp32"))
+    pred = torch.from_numpy(g["ab_y"]).cuda().requires_grad_(True)
+    lap = crit._laplace_gradient(pred, torch.from_numpy(g["ab_x"]).cuda())
+    assert abs(lap.item() - float(g["laplace"])) < 2e-6
+    lap.backward()
+    assert np.abs(pred.grad.cpu().numpy() - g["laplace_grad"]).max() < 1e-9
+    data = {"target_label": torch.from_numpy(gl["labels"]).cuda().long(), "pal_prob": torch.from_numpy(gl["pal"]).cuda(),
+            "ref_prob": torch.from_numpy(gl["ref"]).cuda(), "class_weight": torch.from_numpy(gl["class_weight"]).cuda().float(),
+            "input_gray": torch.from_numpy(g["gray"]).cuda(), "input_color": torch.from_numpy(g["ab_x"]).cuda(),
+            "pred_color": torch.from_numpy(g["ab_y"]).cuda()}
+    d = crit(data, 0)
+    want = 5.0 * float(g["perceptual"]) + float(g["laplace"])
+    assert abs(d["recLoss"].item() - want) < 1e-4 * want
+    with pytest.raises(Exception):
+        loss.AnchorColorProbLoss(hint2regress=True)          # broken in the reference's own training branch: not built
 
 
 def test_vgg_side_ops_reject_bad_shapes():

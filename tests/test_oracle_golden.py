@@ -118,3 +118,7 @@ def test_oracle_perceptual_term_matches_reference_fixture():
             v = float(O.vgg19_loss(convs, rgb_x, rgb_y, ft))
             assert abs(v - float(g["loss_" + ft])) < 1e-5 * abs(float(g["loss_" + ft])) + 1e-7, (ft, v, float(g["loss_" + ft]))
         assert abs(float(O.perceptual_loss(convs, gray, ab_x, ab_y)) - float(g["perceptual"])) < 1e-6
+    pred = ab_y.clone().requires_grad_(True)
+    lap = O.laplace_gradient(pred, ab_x)
+    lap.backward()
+    assert abs(float(lap) - float(g["laplace"])) < 1e-6 and np.abs(pred.grad.numpy() - g["laplace_grad"]).max() < 1e-9
