@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdisco_b200.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "spixel.cu", "tokens.cu", "encoder_stack.cu", "segnet_fused.cu", "colorspace.cu", "loss.cu", "png_host.cu", "conv_narrow.cu", "vgg_ops.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "spixel.cu", "tokens.cu", "encoder_stack.cu", "segnet_fused.cu", "colorspace.cu", "loss.cu", "png_host.cu", "conv_narrow.cu", "vgg_ops.cu", "conv_ts.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -92,4 +92,9 @@ bool conv_narrow_match(const disco_conv_desc* d);
 int64_t conv_narrow_weight_elems(const disco_conv_desc* d);
 int conv_narrow_pack(const disco_conv_desc* d, const float* w32_host, uint16_t* out_host);
 int conv_narrow_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
+// 64 -> 64 stride-1 layers with the A operand in tensor memory (conv_ts.cu); DISCO_TS selects it
+bool conv_ts_match(const disco_conv_desc* d);
+int64_t conv_ts_weight_elems(const disco_conv_desc* d);
+int conv_ts_pack(const disco_conv_desc* d, const float* w32_host, uint16_t* out_host);
+int conv_ts_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st);
 void conv_tc_cache_clear(disco_handle* h);   // frees the cached plans of h->device (caller holds the device guard)

@@ -1733,7 +1733,7 @@ int launch_bn(disco_handle* h, int BN, int MT, const TcParams& P, int grid, cuda
 
 }  // namespace
 
-bool conv_tc_supported(const disco_conv_desc* d) { return conv_narrow_match(d) || build_plan(d).ok; }
+bool conv_tc_supported(const disco_conv_desc* d) { return conv_narrow_match(d) || conv_ts_match(d) || build_plan(d).ok; }
 
 void conv_tc_cache_clear(disco_handle* h) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -1755,7 +1755,7 @@ extern "C" int disco_conv_tc_cache_clear(disco_handle* h) {
 }
 
 extern "C" int disco_conv_tc_supported(disco_handle* h, const disco_conv_desc* d) {
-  return h && d && h->use_tc && (conv_narrow_match(d) || build_plan(d).ok) ? 1 : 0;
+  return h && d && h->use_tc && (conv_narrow_match(d) || conv_ts_match(d) || build_plan(d).ok) ? 1 : 0;
 }
 
 extern "C" int disco_set_tensor_core(disco_handle* h, int enable) {
@@ -1767,6 +1767,7 @@ extern "C" int disco_set_tensor_core(disco_handle* h, int enable) {
 extern "C" int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d) {
   if (!d) return 0;
   if (conv_narrow_match(d)) return conv_narrow_weight_elems(d);
+  if (conv_ts_match(d)) return conv_ts_weight_elems(d);
   Plan p = build_plan(d);
   return p.ok ? (int64_t)p.nkb_total * p.cout_pad * p.KC : 0;
 }
@@ -1775,6 +1776,7 @@ extern "C" int64_t disco_conv_tc_weight_elems(const disco_conv_desc* d) {
 extern "C" int disco_conv_tc_pack_weights(const disco_conv_desc* d, const float* w32, uint16_t* out) {
   DISCO_CHECK_ARG(d && w32 && out, "tc_pack: null pointer");
   if (conv_narrow_match(d)) return conv_narrow_pack(d, w32, out);
+  if (conv_ts_match(d)) return conv_ts_pack(d, w32, out);
   Plan p = build_plan(d);
   DISCO_CHECK_ARG(p.ok, "tc_pack: descriptor not supported by the tensor-core kernel");
   const size_t total = (size_t)p.nkb_total * p.cout_pad * p.KC;
@@ -1820,6 +1822,7 @@ extern "C" int disco_debug_timeline(long long* out) {
 
 int conv_tc_launch(disco_handle* h, const disco_conv_desc* d, cudaStream_t st) {
   if (conv_narrow_match(d)) return conv_narrow_launch(h, d, st);
+  if (conv_ts_match(d)) return conv_ts_launch(h, d, st);
   static bool env_read = false;
   if (!env_read) {
     const char* e = getenv("DISCO_TC_RESIDENT");

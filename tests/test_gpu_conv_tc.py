@@ -291,3 +291,25 @@ def test_narrow_deconv0(B, H, W):
     ref = F.leaky_relu(F.conv_transpose2d(x, w, b, stride=2, padding=1), 0.1)
     out = _run_tc(_lib.DECONV4, 1, [(x, 0, False)], [w], b, 16, 2 * H, 2 * W, act=_lib.ACT_LRELU, slope=0.1)
     _check(out, ref)
+
+
+# ---- 64 -> 64 stride-1 layers: with DISCO_TS=1 these run on the tensor-memory-operand kernel (csrc/conv_ts.cu), otherwise on
+# the resident-weight tcgen05 kernel; the expectations are the same
+@pytest.mark.parametrize("B,H,W,res,post", [(1, 32, 128, False, False), (2, 40, 256, True, True), (1, 19, 200, False, True),
+                                            (3, 8, 64, True, False), (1, 70, 136, False, False), (2, 1, 128, False, False)], ids=str)
+def test_conv_64_to_64_full_resolution_shapes(B, H, W, res, post):
+    from disentangledcolorization_b200 import _lib
+    g = torch.Generator().manual_seed(B * 977 + H * 31 + W)
+    x = _bf(torch.randn(B, 64, H, W, generator=g))
+    w = _bf(torch.randn(64, 64, 3, 3, generator=g) / (64 * 9) ** 0.5)
+    b = torch.randn(64, generator=g) * 0.1
+    r = _bf(torch.randn(B, 64, H, W, generator=g)) if res else None
+    ps, pb = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    ref = F.conv2d(x, w, b, padding=1)
+    if res:
+        ref = ref + r
+    ref = F.leaky_relu(ref, 0.2)
+    if post:
+        ref = ref * ps.view(1, -1, 1, 1) + pb.view(1, -1, 1, 1)
+    out = _run_tc(_lib.CONV3, 1, [(x, 0, False)], [w], b, 64, H, W, act=_lib.ACT_LRELU, slope=0.2, post=(ps, pb) if post else None, res=r)
+    _check(out, ref)
