@@ -21,7 +21,7 @@ EXPORTS = ["disco_version", "disco_abi_size", "disco_last_error", "disco_create"
            "disco_debug_timeline", "disco_token_sample3", "disco_encoder_tail", "disco_conv_tc_cache_clear", "disco_host_choice_rows",
            "disco_encoder_stack", "disco_encoder_stack_pack", "disco_encoder_stack_scratch_elems", "disco_segnet_head", "disco_lab2rgb_u8", "disco_ce_rebalance",
            "disco_spixel_recon_loss", "disco_encode_ab2ind", "disco_host_png_bound", "disco_host_png_encode", "disco_host_png_write",
-           "disco_lab2rgb_norm", "disco_rgb_norm", "disco_maxpool2", "disco_l1_mean", "disco_laplace_l1"]
+           "disco_lab2rgb_norm", "disco_rgb_norm", "disco_maxpool2", "disco_l1_mean", "disco_laplace_l1", "disco_spixel_ids"]
 
 
 class ConvSrc(C.Structure):
@@ -101,6 +101,7 @@ def load():
     lib.disco_l1_mean.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p]
     lib.disco_laplace_l1.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 3
+    lib.disco_spixel_ids.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2
     lib.disco_host_png_bound.argtypes = [C.c_int, C.c_int]
     lib.disco_host_png_bound.restype = C.c_longlong
     lib.disco_host_png_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]

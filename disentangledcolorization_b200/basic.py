@@ -149,3 +149,29 @@ def lab2rgb(lab_rs, l_mean=50, l_norm=50, ab_norm=110):
         _lib.check(handle.lib.disco_lab2rgb_norm(handle.h, _p(gray), _p(ab), N, H, W, _p(out), None, _lib.F32, 3, None, None, stream),
                    "disco_lab2rgb_norm")
     return out
+
+
+def init_spixel_grid(img_height, img_width, spixel_size=16):
+    """reference models/basic.py:221-262: (9,H,W) float map of the ids of the 9 neighbour cells of every pixel's cell (edge
+    replicated) and the (2,H,W) pixel coordinate map (x first).  Host-side numpy, as in the reference."""
+    n_h, n_w = int(np.floor(img_height / spixel_size)), int(np.floor(img_width / spixel_size))
+    sp_h, sp_w = int(img_height / (1.0 * n_h)), int(img_width / (1.0 * n_w))
+    cells = np.pad(np.int32(np.arange(0, n_w * n_h).reshape((n_h, n_w))), ((1, 1), (1, 1)), mode="edge")
+    shifts = [cells[dy:dy + n_h, dx:dx + n_w] for dy in range(3) for dx in range(3)]     # top-left ... bottom-right
+    grid = np.repeat(np.repeat(np.stack(shifts, 0), sp_h, axis=1), sp_w, axis=2)
+    yy, xx = np.meshgrid(np.arange(0, img_height, 1), np.arange(0, img_width, 1), indexing="ij")
+    return torch.from_numpy(grid).float(), torch.from_numpy(np.stack([xx, yy], 0)).float()
+
+
+def split_spixels(assign_map, sp_size=16):
+    """`split_spixels` of the reference's SpixelSeg inference script (main/spixelseg/inference.py:67-75): winner-take-all
+    super-pixel id map (N,1,H,W) int32 from the (N,9,H,W) assignment map, on the init_spixel_grid ids (disco_spixel_ids)."""
+    if assign_map.dim() != 4 or assign_map.shape[1] != 9:
+        raise _lib.DiscoError(f"split_spixels: assignment map must be (N,9,H,W), got {tuple(assign_map.shape)}")
+    handle, stream = _ctx(assign_map)
+    with torch.cuda.device(assign_map.device):
+        prob = assign_map.detach().float().contiguous()
+        N, _, H, W = prob.shape
+        ids = torch.empty(N, 1, H, W, dtype=torch.int32, device=prob.device)
+        _lib.check(handle.lib.disco_spixel_ids(handle.h, _p(prob), N, H, W, int(sp_size), _p(ids), stream), "disco_spixel_ids")
+    return ids

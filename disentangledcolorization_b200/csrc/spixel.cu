@@ -484,3 +484,39 @@ extern "C" int disco_upfeat(disco_handle* h, int dtype, const float* tokens, con
   DISCO_LAUNCH_CHECK(h);
   return DISCO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// split_spixels of the SpixelSeg inference script (reference main/spixelseg/inference.py:67-75): winner-take-all super-pixel
+// id per pixel.  The 9-channel neighbour-id map of basic.init_spixel_grid (models/basic.py:221-251: cell ids with edge
+// replication) is evaluated on the fly; like the reference, ids of ALL channels that equal the maximum are summed.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void spixel_ids_kernel(const float* __restrict__ prob, int B, int H, int W, int sp, int32_t* __restrict__ ids) {
+  const size_t plane = (size_t)H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * plane) return;
+  const size_t n = idx / plane, p = idx - n * plane;
+  const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+  const int nh = H / sp, nw = W / sp, cy = y / sp, cx = x / sp;
+  const float* pr = prob + n * 9 * plane + p;
+  float v[9], mx = -3.4e38f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { v[k] = pr[(size_t)k * plane]; mx = fmaxf(mx, v[k]); }
+  int id = 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    if (v[k] == mx) id += min(max(cy + k / 3 - 1, 0), nh - 1) * nw + min(max(cx + k % 3 - 1, 0), nw - 1);
+  ids[idx] = id;
+}
+}  // namespace
+
+extern "C" int disco_spixel_ids(disco_handle* h, const float* prob, int batch, int H, int W, int sp, int32_t* ids, void* stream) {
+  DISCO_CHECK_ARG(h && prob && ids, "spixel_ids: null pointer");
+  DISCO_CHECK_ARG(batch > 0 && sp > 0 && H >= sp && W >= sp && H % sp == 0 && W % sp == 0,
+                  "spixel_ids: H, W must be positive multiples of the super-pixel size (got %dx%d, %d)", H, W, sp);
+  DiscoDeviceGuard guard(h);
+  const size_t n = (size_t)batch * H * W;
+  spixel_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prob, batch, H, W, sp, ids);
+  DISCO_LAUNCH_CHECK(h);
+  return DISCO_OK;
+}

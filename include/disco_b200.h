@@ -292,6 +292,11 @@ int disco_lab2rgb_u8(disco_handle* h, const float* gray, const float* ab, int ba
 int disco_host_choice_rows(uint32_t* mt_key, int32_t* mt_pos, int S, int K, int rows, int keep_lo, int keep_hi,
                            int32_t* out);
 
+/* split_spixels of main/spixelseg/inference.py:67-75 on the neighbour-id grid of basic.init_spixel_grid
+ * (models/basic.py:221-251): ids[n,y,x] = sum over the channels k with prob[n,k,y,x] == max_k prob of the id of the k-th
+ * neighbour cell (edge-replicated) of the sp x sp cell that holds (y, x).  prob fp32 [B,9,H,W], ids int32 [B,1,H,W]. */
+int disco_spixel_ids(disco_handle* h, const float* prob, int batch, int H, int W, int sp, int32_t* ids, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Perceptual-loss side ops (config 5; AnchorColorProbLoss._perceptual_loss, models/loss.py:45-49 and VGG19Loss,
  * models/loss.py:138-223).  The VGG19 convolutions themselves are disco_conv calls (3x3, bias, ReLU).

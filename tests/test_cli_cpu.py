@@ -114,3 +114,25 @@ def test_native_png_writer_rejects_bad_input(tmp_path):
         _lib.png_encode(np.zeros((4, 8, 3), np.uint8)[:, ::2])
     with pytest.raises(RuntimeError):
         _lib.png_write(str(tmp_path / "no_such_dir" / "a.png"), np.zeros((4, 4, 3), np.uint8))
+
+
+def test_spixel_cli_flags_and_grid_match_reference():
+    """main/spixelseg/inference.py:130-137 flag surface; basic.init_spixel_grid == the reference's (models/basic.py:221-262)
+    when the reference is present (it is not on the GPU box)."""
+    import torch
+    from disentangledcolorization_b200 import basic, spixel_inference
+    d = spixel_inference.build_parser().parse_args([])
+    assert (d.name, d.psize, d.model) == ("result", 16, "SpixelSeg")
+    ids, coords = basic.init_spixel_grid(64, 96, 16)
+    assert tuple(ids.shape) == (9, 64, 96) and tuple(coords.shape) == (2, 64, 96)
+    assert ids[4, 17, 33] == 1 * 6 + 2 and ids[0, 0, 0] == 0 and ids[8, 63, 95] == 3 * 6 + 5     # centre channel = own cell; edges replicate
+    assert coords[0, 5, 9] == 9 and coords[1, 5, 9] == 5
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_harness
+    if ref_harness.available():
+        ref_harness.load()
+        import basic as ref_basic
+        for H, W, sp in ((256, 256, 16), (64, 96, 16), (128, 64, 8)):
+            a, b = ref_basic.init_spixel_grid(H, W, sp)
+            c, e = basic.init_spixel_grid(H, W, sp)
+            assert torch.equal(a, c) and torch.equal(b, e)
