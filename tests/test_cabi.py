@@ -51,3 +51,20 @@ def test_product_path_fails_loudly_without_cuda():
     m = model.AnchorColorProb(n_clusters=8, enhanced=True).eval()
     with pytest.raises(_lib.DiscoError):
         m(torch.zeros(1, 1, 32, 32), torch.zeros(1, 2, 32, 32), True, 0)
+
+
+def test_loss_and_helper_modules_fail_loudly_without_cuda():
+    """The training-side terms and the super-pixel helpers have no CPU path either."""
+    import pytest
+    import torch
+    from disentangledcolorization_b200 import basic, loss, _lib
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(_lib.DiscoError):
+        basic.lab2rgb(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(_lib.DiscoError):
+        basic.split_spixels(torch.full((1, 9, 16, 16), 1.0 / 9))
+    with pytest.raises(_lib.DiscoError):
+        loss.AnchorColorProbLoss()._laplace_gradient(torch.zeros(1, 2, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(_lib.DiscoError):
+        loss.SPixelLoss(psize=16)({"pred_prob": torch.full((1, 9, 16, 16), 1.0 / 9), "target_feat": torch.zeros(1, 5, 16, 16)}, 0)
