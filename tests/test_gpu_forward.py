@@ -283,3 +283,22 @@ def test_pipeline_double_buffered_matches_direct_forward(synth_sd):
     for i, (x, y) in enumerate(zip(got, direct)):
         assert torch.equal(x, y), f"step {i}: pipelined result differs from the direct forward"
     assert pipe.h2d_bytes == B * 3 * H * W * 4 and pipe.d2h_bytes == B * 2 * H * W * 4
+
+
+@pytest.mark.parametrize("H,W", [(80, 112), (48, 208), (16, 16)], ids=str)
+def test_bf16_affinity_on_ragged_tile_sizes_matches_oracle(synth_sd, H, W):
+    """SpixelNet in bf16 on sizes that leave partial 32 x 16 tiles in the mma.sync decoder-tail kernels (csrc/conv_narrow.cu)
+    and partial 128-pixel tiles in the tcgen05 kernels: the affinity map stays within the bf16 storage error of the fp32
+    oracle and sums to one.  Bounds as measured for the fused head (test_gpu_ops): max 8e-2, mean 2e-3."""
+    import disco_oracle as O
+    from disentangledcolorization_b200 import model, synth
+    gray = torch.from_numpy(synth.make_gray(3, H, W, seed=H + W))
+    seg = model.SpixelSeg()
+    seg.load_state_dict({k[len("segnet."):]: v for k, v in synth_sd.items() if k.startswith("segnet.")})
+    got = seg.cuda().eval()(gray.cuda()).cpu()                 # precision: bf16 (default)
+    with torch.no_grad():
+        want = O.spixelnet(synth_sd, gray)
+    assert tuple(got.shape) == (3, 9, H, W) and torch.isfinite(got).all()
+    d = (got - want).abs()
+    assert float(d.max()) < 8e-2 and float(d.mean()) < 2e-3, (float(d.max()), float(d.mean()))
+    assert float((got.sum(1) - 1).abs().max()) < 1e-5
